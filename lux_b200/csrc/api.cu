@@ -1,0 +1,1086 @@
+// api.cu — C ABI of libluxb (include/lux_b200.h) and the thin per-rank host runtime behind it.
+// Replaces, for the hot path only: Graph::Graph + load/scan/init tasks, pull_app_task_impl / push_app_task_impl,
+// the app driver loops and LuxMapper's placement (see the citations in lux_b200.h).
+// Product code: nothing here may include, link or call oracle/.
+#include <cub/cub.cuh>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <new>
+
+#include "build.cuh"
+#include "cf.cuh"
+#include "pull.cuh"
+#include "push.cuh"
+#include "runtime.cuh"
+
+using namespace luxb;
+
+// ------------------------------------------------------------------------------------------------------------
+namespace luxb {
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace luxb
+
+#define LUXB_ARG(cond, ...)             \
+  do {                                  \
+    if (!(cond)) {                      \
+      set_error(__VA_ARGS__);           \
+      return LUXB_ERR_ARG;              \
+    }                                   \
+  } while (0)
+
+#define LUXB_NCCL(expr)                                                                              \
+  do {                                                                                               \
+    ncclResult_t _r = (expr);                                                                        \
+    if (_r != ncclSuccess) {                                                                         \
+      set_error("NCCL error %s at %s:%d: %s", #expr, __FILE__, __LINE__, nccl().GetErrorString(_r)); \
+      return LUXB_ERR_COMM;                                                                          \
+    }                                                                                                \
+  } while (0)
+
+using PullShapeDefault = PullShape<128, 17, 2>;
+
+static inline int grid_for(uint64_t n, int threads, int cap) {
+  uint64_t b = (n + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > (uint64_t)cap) b = cap;
+  return (int)b;
+}
+
+template <class T>
+static int dmalloc(T** p, uint64_t count) {
+  void* q = nullptr;
+  LUXB_CUDA(cudaMalloc(&q, std::max<uint64_t>(count, 1) * sizeof(T) + 256));
+  *p = reinterpret_cast<T*>(q);
+  return 0;
+}
+
+// ---- the reference partitioner on the host (pull_model.inl:108-131); same cut rule as partition_kernel -------
+static int host_partition(uint32_t nv, uint64_t ne, const uint64_t* row_end, int P, uint32_t* rl, uint32_t* np,
+                          uint64_t* cl) {
+  uint64_t cap = (ne + P - 1) / P;
+  uint32_t left = 0;
+  int count = 0, found_adjust = 0;
+  while (left < nv && count < P) {
+    uint64_t base = left == 0 ? 0 : row_end[left - 1];
+    const uint64_t* first = std::upper_bound(row_end + left, row_end + nv, base + cap);  // first row_end[v] > base+cap
+    uint32_t v = (uint32_t)(first - row_end);
+    if (v < nv) {
+      rl[count] = left; np[count] = v - left + 1; cl[count] = base; ++count;
+      left = v + 1;
+    } else {
+      // the reference emits the remainder only if it holds edges (pull_model.inl:128-130) and would then assert
+      // on the partition count; we always keep trailing zero-in-degree vertices so that none is dropped
+      if (row_end[nv - 1] - base == 0) --found_adjust;
+      rl[count] = left; np[count] = nv - left; cl[count] = base; ++count;
+      left = nv;
+    }
+  }
+  int found = count + found_adjust;
+  for (int p = count; p < P; ++p) { rl[p] = nv; np[p] = 0; cl[p] = ne; }
+  return found;
+}
+
+static int check_config(const luxb_config* cfg) {
+  LUXB_ARG(cfg != nullptr, "config is NULL");
+  LUXB_ARG(cfg->app >= LUXB_PAGERANK && cfg->app <= LUXB_COLFILTER, "unknown app %d", (int)cfg->app);
+  LUXB_ARG(cfg->nranks >= 1 && cfg->nranks <= LUXB_MAX_PARTS, "nranks %d out of range [1,%d]", cfg->nranks, LUXB_MAX_PARTS);
+  LUXB_ARG(cfg->rank >= 0 && cfg->rank < cfg->nranks, "rank %d out of range", cfg->rank);
+  return 0;
+}
+
+static int graph_begin(const luxb_config* cfg, luxb_graph** out) {
+  LUXB_TRY(check_config(cfg));
+  LUXB_ARG(out != nullptr, "out is NULL");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device available (%s): libluxb has no CPU fallback", cudaGetErrorString(e));
+    return LUXB_ERR_CUDA;
+  }
+  LUXB_ARG(cfg->device >= 0 && cfg->device < ndev, "device %d out of range (have %d)", cfg->device, ndev);
+  LUXB_CUDA(cudaSetDevice(cfg->device));
+  luxb_graph* g = new (std::nothrow) luxb_graph();
+  if (!g) { set_error("out of host memory"); return LUXB_ERR_NOMEM; }
+  g->cfg = *cfg;
+  g->P = cfg->nranks;
+  *out = g;
+  LUXB_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+  LUXB_CUDA(cudaEventCreate(&g->ev_begin));
+  LUXB_CUDA(cudaEventCreate(&g->ev_end));
+  LUXB_CUDA(cudaDeviceGetAttribute(&g->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
+  return 0;
+}
+
+static void set_partition_derived(luxb_graph* g) {
+  int r = g->cfg.rank;
+  g->row_left = g->rl[r];
+  g->n_part = g->np[r];
+  g->col_left = g->cl[r];
+  uint64_t next = (r + 1 < g->P) ? g->cl[r + 1] : g->ne;
+  if (g->np[r] == 0) next = g->col_left;
+  g->e_part = next - g->col_left;
+  uint64_t off = 0;
+  for (int p = 0; p < g->P; ++p) {
+    uint32_t span = g->np[p] ? g->np[p] - 1 : 0;          // R - L
+    g->cap[p] = span / 16 + 100;                          // push_model.inl:393
+    g->slot_off[p] = off;
+    g->slot_bytes[p] = ((8 + (uint64_t)g->cap[p] * 8) + 15) & ~15ull;  // header + ids + labels
+    off += g->slot_bytes[p];
+  }
+  g->fq_total = off;
+}
+
+// after d_row_end / d_src are in place: merge-path tile table + per-tile partial buffers
+static int finish_layout(luxb_graph* g) {
+  uint64_t total = (uint64_t)g->n_part + g->e_part;
+  uint64_t nt = (total + PullShapeDefault::kTile - 1) / PullShapeDefault::kTile;
+  LUXB_ARG(nt < 0xFFFFFFFFull, "partition too large for the tile table");
+  g->n_tiles = (uint32_t)nt;
+  LUXB_TRY(dmalloc(&g->d_tile_v, (uint64_t)g->n_tiles + 2));
+  tile_table_kernel<<<grid_for((uint64_t)g->n_tiles + 1, 256, 1 << 20), 256, 0, g->stream>>>(
+      g->d_row_end, g->n_part, g->e_part, PullShapeDefault::kTile, g->n_tiles, g->d_tile_v);
+  LUXB_CUDA(cudaGetLastError());
+  LUXB_TRY(dmalloc((uint32_t**)&g->d_head, (uint64_t)g->n_tiles + 1));
+  LUXB_TRY(dmalloc((uint32_t**)&g->d_tail, (uint64_t)g->n_tiles + 1));
+  LUXB_TRY(dmalloc(&g->d_counters, 4));
+  LUXB_CUDA(cudaMemsetAsync(g->d_counters, 0, 4 * sizeof(unsigned long long), g->stream));
+  LUXB_CUDA(cudaStreamSynchronize(g->stream));
+  return 0;
+}
+
+static int validate_row_end(uint32_t nv, uint64_t ne, const uint64_t* row_end) {
+  LUXB_ARG(nv >= 1, "graph has no vertices");
+  for (uint32_t v = 1; v < nv; ++v)
+    LUXB_ARG(row_end[v] >= row_end[v - 1], "row_end not non-decreasing at vertex %u (pull_model.inl:100-101)", v);
+  LUXB_ARG(row_end[nv - 1] == ne, "row_end[nv-1] (%llu) != ne (%llu) (pull_model.inl:102)",
+           (unsigned long long)row_end[nv - 1], (unsigned long long)ne);
+  return 0;
+}
+
+// upload this rank's slice given host pointers to ITS portion of row_end (absolute) / src / weight
+static int upload_slice(luxb_graph* g, const uint64_t* row_end_slice_abs, const uint32_t* src_slice,
+                        const int32_t* weight_slice) {
+  LUXB_TRY(dmalloc(&g->d_row_end, (uint64_t)g->n_part + 4));
+  LUXB_TRY(dmalloc(&g->d_src, g->e_part + 8));
+  uint64_t* d_tmp = nullptr;
+  LUXB_TRY(dmalloc(&d_tmp, (uint64_t)g->n_part + 1));
+  if (g->n_part)
+    LUXB_CUDA(cudaMemcpyAsync(d_tmp, row_end_slice_abs, (size_t)g->n_part * 8, cudaMemcpyHostToDevice, g->stream));
+  rowend_rel_kernel<<<grid_for((uint64_t)g->n_part + 4, 256, 4096), 256, 0, g->stream>>>(d_tmp, 0, g->n_part, g->col_left,
+                                                                                        g->d_row_end);
+  LUXB_CUDA(cudaGetLastError());
+  LUXB_CUDA(cudaMemsetAsync(g->d_src, 0, (g->e_part + 8) * 4, g->stream));
+  if (g->e_part) LUXB_CUDA(cudaMemcpyAsync(g->d_src, src_slice, g->e_part * 4, cudaMemcpyHostToDevice, g->stream));
+  if (g->weighted) {
+    LUXB_TRY(dmalloc(&g->d_weight, g->e_part + 8));
+    LUXB_CUDA(cudaMemsetAsync(g->d_weight, 0, (g->e_part + 8) * 4, g->stream));
+    if (g->e_part) LUXB_CUDA(cudaMemcpyAsync(g->d_weight, weight_slice, g->e_part * 4, cudaMemcpyHostToDevice, g->stream));
+  }
+  LUXB_CUDA(cudaStreamSynchronize(g->stream));
+  LUXB_CUDA(cudaFree(d_tmp));
+  return finish_layout(g);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* luxb_last_error(void) { return g_err; }
+const char* luxb_version(void) { return "lux_b200 0.1 (sm_100a)"; }
+
+int luxb_partition_csc(luxb_vid nv, luxb_eid ne, const luxb_eid* row_end, int P, luxb_vid* row_left, luxb_vid* row_right,
+                       luxb_eid* col_left) {
+  LUXB_ARG(row_end && row_left && row_right && col_left, "NULL argument");
+  LUXB_ARG(P >= 1 && P <= LUXB_MAX_PARTS, "P out of range");
+  LUXB_TRY(validate_row_end(nv, ne, row_end));
+  uint32_t np[LUXB_MAX_PARTS];
+  int found = host_partition(nv, ne, row_end, P, row_left, np, col_left);
+  for (int p = 0; p < P; ++p) row_right[p] = row_left[p] + np[p] - 1;  // empty: row_left - 1
+  return found;
+}
+
+int luxb_open_csc(const luxb_csc* csc, const luxb_config* cfg, luxb_graph** out) {
+  LUXB_ARG(csc && csc->row_end && (csc->src || csc->ne == 0), "csc arrays are NULL");
+  LUXB_TRY(check_config(cfg));
+  LUXB_ARG(cfg->app != LUXB_COLFILTER || csc->weight, "col_filter needs edge weights (EDGE_WEIGHT, col_filter/app.h:22)");
+  LUXB_TRY(validate_row_end(csc->nv, csc->ne, csc->row_end));
+  for (uint64_t e = 0; e < csc->ne; ++e) LUXB_ARG(csc->src[e] < csc->nv, "src[%llu] out of range", (unsigned long long)e);
+  luxb_graph* g = nullptr;
+  int rc = graph_begin(cfg, &g);
+  if (rc) { if (g) luxb_close(g); return rc; }
+  g->nv = csc->nv;
+  g->ne = csc->ne;
+  g->weighted = cfg->app == LUXB_COLFILTER;
+  g->parts_found = host_partition(g->nv, g->ne, csc->row_end, g->P, g->rl, g->np, g->cl);
+  set_partition_derived(g);
+  rc = upload_slice(g, csc->row_end + (g->n_part ? g->row_left : 0), csc->src + g->col_left,
+                    g->weighted ? csc->weight + g->col_left : nullptr);
+  if (rc) { luxb_close(g); return rc; }
+  *out = g;
+  return 0;
+}
+
+int luxb_open_file(const char* path, const luxb_config* cfg, luxb_graph** out) {
+  LUXB_ARG(path != nullptr, "path is NULL");
+  LUXB_TRY(check_config(cfg));
+  FILE* f = fopen(path, "rb");
+  if (!f) { set_error("cannot open %s", path); return LUXB_ERR_IO; }
+  uint32_t nv = 0;
+  uint64_t ne = 0;
+  if (fread(&nv, 4, 1, f) != 1 || fread(&ne, 8, 1, f) != 1 || nv == 0) {  // FILE_HEADER_SIZE, core/graph.h:32
+    fclose(f);
+    set_error("%s: bad .lux header", path);
+    return LUXB_ERR_IO;
+  }
+  std::vector<uint64_t> row_end(nv);
+  if (fread(row_end.data(), 8, nv, f) != nv) { fclose(f); set_error("%s: truncated row_end", path); return LUXB_ERR_IO; }
+  int rc = validate_row_end(nv, ne, row_end.data());
+  if (rc) { fclose(f); return rc; }
+  luxb_graph* g = nullptr;
+  rc = graph_begin(cfg, &g);
+  if (rc) { fclose(f); if (g) luxb_close(g); return rc; }
+  g->nv = nv;
+  g->ne = ne;
+  g->weighted = cfg->app == LUXB_COLFILTER;
+  g->parts_found = host_partition(nv, ne, row_end.data(), g->P, g->rl, g->np, g->cl);
+  set_partition_derived(g);
+  // this rank's slice only — same seeks as pull_load_task_impl (pull_model.inl:294-318)
+  std::vector<uint32_t> src(g->e_part ? g->e_part : 1);
+  std::vector<int32_t> w(g->weighted && g->e_part ? g->e_part : 1);
+  bool ok = fseeko(f, (off_t)(12 + 8 * (uint64_t)nv + 4 * g->col_left), SEEK_SET) == 0 &&
+            fread(src.data(), 4, g->e_part, f) == g->e_part;
+  if (ok && g->weighted)
+    ok = fseeko(f, (off_t)(12 + 8 * (uint64_t)nv + 4 * ne + 4 * g->col_left), SEEK_SET) == 0 &&
+         fread(w.data(), 4, g->e_part, f) == g->e_part;
+  fclose(f);
+  if (!ok) { luxb_close(g); set_error("%s: truncated edge data", path); return LUXB_ERR_IO; }
+  for (uint64_t e = 0; e < g->e_part; ++e)
+    if (src[e] >= nv) { luxb_close(g); set_error("%s: source id out of range", path); return LUXB_ERR_ARG; }
+  rc = upload_slice(g, row_end.data() + (g->n_part ? g->row_left : 0), src.data(), g->weighted ? w.data() : nullptr);
+  if (rc) { luxb_close(g); return rc; }
+  *out = g;
+  return 0;
+}
+
+static int open_generated(const GenSpec& spec, const luxb_config* cfg, luxb_graph** out) {
+  luxb_graph* g = nullptr;
+  int rc = graph_begin(cfg, &g);
+  if (rc) { if (g) luxb_close(g); return rc; }
+  auto fail = [&](int code) { luxb_close(g); return code; };
+  g->nv = spec.nv;
+  g->ne = spec.ne;
+  g->weighted = cfg->app == LUXB_COLFILTER;
+  const int gen_grid = g->num_sms * 16;
+  // 1. in-degree histogram over the whole edge stream -> global row_end (u64) by an inclusive scan
+  uint32_t* d_indeg = nullptr;
+  uint64_t* d_row_end_g = nullptr;
+  if ((rc = dmalloc(&d_indeg, spec.nv))) return fail(rc);
+  if ((rc = dmalloc(&d_row_end_g, spec.nv))) return fail(rc);
+#define GEN_CUDA(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { set_error("CUDA error %s: %s", #x, cudaGetErrorString(_e)); return fail(LUXB_ERR_CUDA); } } while (0)
+  GEN_CUDA(cudaMemsetAsync(d_indeg, 0, (size_t)spec.nv * 4, g->stream));
+  gen_count_indeg_kernel<<<gen_grid, 256, 0, g->stream>>>(spec, d_indeg);
+  widen_u32_to_u64_kernel<<<gen_grid, 256, 0, g->stream>>>(d_indeg, d_row_end_g, spec.nv);
+  size_t tmp_bytes = 0;
+  GEN_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, d_row_end_g, d_row_end_g, (int)spec.nv, g->stream));
+  void* d_tmp = nullptr;
+  GEN_CUDA(cudaMalloc(&d_tmp, tmp_bytes + 256));
+  GEN_CUDA(cub::DeviceScan::InclusiveSum(d_tmp, tmp_bytes, d_row_end_g, d_row_end_g, (int)spec.nv, g->stream));
+  // 2. partition table (reference greedy split), on the device
+  uint32_t* d_pt = nullptr;  // rl[P], np[P]
+  uint64_t* d_cl = nullptr;
+  int* d_cnt = nullptr;
+  if ((rc = dmalloc(&d_pt, 2 * LUXB_MAX_PARTS))) return fail(rc);
+  if ((rc = dmalloc(&d_cl, LUXB_MAX_PARTS))) return fail(rc);
+  if ((rc = dmalloc(&d_cnt, 1))) return fail(rc);
+  partition_kernel<<<1, 1, 0, g->stream>>>(d_row_end_g, spec.nv, spec.ne, g->P, d_pt, d_pt + LUXB_MAX_PARTS, d_cl, d_cnt);
+  GEN_CUDA(cudaMemcpyAsync(g->rl, d_pt, g->P * 4, cudaMemcpyDeviceToHost, g->stream));
+  GEN_CUDA(cudaMemcpyAsync(g->np, d_pt + LUXB_MAX_PARTS, g->P * 4, cudaMemcpyDeviceToHost, g->stream));
+  GEN_CUDA(cudaMemcpyAsync(g->cl, d_cl, g->P * 8, cudaMemcpyDeviceToHost, g->stream));
+  GEN_CUDA(cudaMemcpyAsync(&g->parts_found, d_cnt, 4, cudaMemcpyDeviceToHost, g->stream));
+  GEN_CUDA(cudaStreamSynchronize(g->stream));
+  set_partition_derived(g);
+  // 3. local row_end (relative + sentinels)
+  if ((rc = dmalloc(&g->d_row_end, (uint64_t)g->n_part + 4))) return fail(rc);
+  rowend_rel_kernel<<<grid_for((uint64_t)g->n_part + 4, 256, 4096), 256, 0, g->stream>>>(d_row_end_g, g->row_left, g->n_part,
+                                                                                        g->col_left, g->d_row_end);
+  GEN_CUDA(cudaGetLastError());
+  GEN_CUDA(cudaStreamSynchronize(g->stream));
+  GEN_CUDA(cudaFree(d_indeg));
+  GEN_CUDA(cudaFree(d_row_end_g));
+  GEN_CUDA(cudaFree(d_tmp));
+  GEN_CUDA(cudaFree(d_pt));
+  GEN_CUDA(cudaFree(d_cl));
+  GEN_CUDA(cudaFree(d_cnt));
+  // 4. this partition's edges: regenerate the stream, keep keys (dst_local << 32 | src), radix sort -> canonical CSC
+  uint64_t *d_keys = nullptr, *d_keys_alt = nullptr;
+  unsigned long long* d_cursor = nullptr;
+  if ((rc = dmalloc(&d_keys, g->e_part))) return fail(rc);
+  if ((rc = dmalloc(&d_keys_alt, g->e_part))) return fail(rc);
+  if ((rc = dmalloc(&d_cursor, 1))) return fail(rc);
+  GEN_CUDA(cudaMemsetAsync(d_cursor, 0, 8, g->stream));
+  gen_emit_keys_kernel<<<gen_grid, 256, 0, g->stream>>>(spec, g->row_left, g->n_part, d_cursor, d_keys, g->e_part);
+  GEN_CUDA(cudaGetLastError());
+  unsigned long long emitted = 0;
+  GEN_CUDA(cudaMemcpyAsync(&emitted, d_cursor, 8, cudaMemcpyDeviceToHost, g->stream));
+  GEN_CUDA(cudaStreamSynchronize(g->stream));
+  if (emitted != g->e_part) {
+    set_error("generator emitted %llu edges for this partition, expected %llu", emitted, (unsigned long long)g->e_part);
+    return fail(LUXB_ERR_STATE);
+  }
+  int vbits = 1;
+  while ((1ull << vbits) < (uint64_t)spec.nv) ++vbits;
+  int pbits = 1;
+  while ((1ull << pbits) < (uint64_t)g->n_part + 1) ++pbits;
+  cub::DoubleBuffer<uint64_t> keys(d_keys, d_keys_alt);
+  tmp_bytes = 0;
+  GEN_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys, (long long)g->e_part, 0, 32 + pbits, g->stream));
+  GEN_CUDA(cudaMalloc(&d_tmp, tmp_bytes + 256));
+  GEN_CUDA(cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, keys, (long long)g->e_part, 0, 32 + pbits, g->stream));
+  if ((rc = dmalloc(&g->d_src, g->e_part + 8))) return fail(rc);
+  GEN_CUDA(cudaMemsetAsync(g->d_src, 0, (g->e_part + 8) * 4, g->stream));
+  if (g->weighted) {
+    if ((rc = dmalloc(&g->d_weight, g->e_part + 8))) return fail(rc);
+    GEN_CUDA(cudaMemsetAsync(g->d_weight, 0, (g->e_part + 8) * 4, g->stream));
+  }
+  keys_to_src_kernel<<<gen_grid, 256, 0, g->stream>>>(keys.Current(), g->e_part, g->d_src, g->d_weight, spec.seed, g->row_left);
+  GEN_CUDA(cudaGetLastError());
+  GEN_CUDA(cudaStreamSynchronize(g->stream));
+  GEN_CUDA(cudaFree(d_keys));
+  GEN_CUDA(cudaFree(d_keys_alt));
+  GEN_CUDA(cudaFree(d_cursor));
+  GEN_CUDA(cudaFree(d_tmp));
+#undef GEN_CUDA
+  (void)vbits;
+  rc = finish_layout(g);
+  if (rc) return fail(rc);
+  *out = g;
+  return 0;
+}
+
+int luxb_open_rmat(int scale, luxb_vid nv, luxb_eid ne, uint64_t seed, const luxb_config* cfg, luxb_graph** out) {
+  LUXB_TRY(check_config(cfg));
+  LUXB_ARG(scale >= 1 && scale <= 31, "scale out of range");
+  LUXB_ARG(nv >= 1 && (uint64_t)nv <= (1ull << scale), "nv must be in [1, 2^scale]");
+  LUXB_ARG(cfg->app != LUXB_COLFILTER, "use luxb_open_bipartite for col_filter");
+  GenSpec s{};
+  s.kind = 0; s.scale = scale; s.nv = nv; s.ne = ne; s.seed = seed;
+  return open_generated(s, cfg, out);
+}
+
+int luxb_open_bipartite(luxb_vid users, luxb_vid items, luxb_eid ratings, uint64_t seed, const luxb_config* cfg,
+                        luxb_graph** out) {
+  LUXB_TRY(check_config(cfg));
+  LUXB_ARG(users >= 1 && items >= 1, "users and items must be positive");
+  GenSpec s{};
+  s.kind = 1; s.nv = users + items; s.ne = 2 * ratings; s.seed = seed; s.users = users; s.items = items;
+  return open_generated(s, cfg, out);
+}
+
+int luxb_graph_info(const luxb_graph* g, luxb_vid* nv, luxb_eid* ne, int* nranks) {
+  LUXB_ARG(g != nullptr, "graph is NULL");
+  if (nv) *nv = g->nv;
+  if (ne) *ne = g->ne;
+  if (nranks) *nranks = g->P;
+  return 0;
+}
+
+int luxb_partition_bounds(const luxb_graph* g, luxb_vid* row_left, luxb_vid* row_right, luxb_eid* col_left,
+                          uint64_t* fq_left, uint64_t* fq_right) {
+  LUXB_ARG(g != nullptr, "graph is NULL");
+  uint64_t fsize = 0;
+  for (int p = 0; p < g->P; ++p) {
+    if (row_left) row_left[p] = g->rl[p];
+    if (row_right) row_right[p] = g->rl[p] + g->np[p] - 1;
+    if (col_left) col_left[p] = g->cl[p];
+    uint64_t bytes = 8 + (uint64_t)g->cap[p] * 4;  // sizeof(FrontierHeader) + mySlots * sizeof(V_ID)
+    if (fq_left) fq_left[p] = fsize;
+    fsize += bytes;
+    if (fq_right) fq_right[p] = fsize - 1;
+  }
+  return g->parts_found;
+}
+
+// ---- communicator ------------------------------------------------------------------------------------------
+int luxb_comm_unique_id(char id[LUXB_UNIQUE_ID_BYTES]) {
+  LUXB_ARG(id != nullptr, "id is NULL");
+  const char* err = nccl().load();
+  if (err) { set_error("%s", err); return LUXB_ERR_COMM; }
+  ncclUniqueId uid;
+  LUXB_NCCL(nccl().GetUniqueId(&uid));
+  memcpy(id, &uid, LUXB_UNIQUE_ID_BYTES);
+  return 0;
+}
+
+int luxb_comm_init(luxb_graph* g, const char id[LUXB_UNIQUE_ID_BYTES]) {
+  LUXB_ARG(g != nullptr, "graph is NULL");
+  if (g->P == 1) return 0;
+  LUXB_ARG(id != nullptr, "id is NULL");
+  LUXB_ARG(g->comm == nullptr, "communicator already initialised");
+  const char* err = nccl().load();
+  if (err) { set_error("%s", err); return LUXB_ERR_COMM; }
+  LUXB_CUDA(cudaSetDevice(g->cfg.device));
+  ncclUniqueId uid;
+  memcpy(&uid, id, LUXB_UNIQUE_ID_BYTES);
+  LUXB_NCCL(nccl().CommInitRank(&g->comm, g->P, uid, g->cfg.rank));
+  return 0;
+}
+
+struct P2PBlob {
+  cudaIpcMemHandle_t val[2];
+};
+
+int luxb_p2p_export(luxb_graph* g, void* blob, size_t* blob_bytes) {
+  LUXB_ARG(g && blob_bytes, "NULL argument");
+  if (!blob) { *blob_bytes = sizeof(P2PBlob); return 0; }
+  LUXB_ARG(*blob_bytes >= sizeof(P2PBlob), "blob too small");
+  if (!g->inited) { set_error("luxb_p2p_export: call luxb_init first"); return LUXB_ERR_STATE; }
+  P2PBlob b;
+  memset(&b, 0, sizeof(b));
+  LUXB_CUDA(cudaSetDevice(g->cfg.device));
+  for (int k = 0; k < 2; ++k)
+    if (g->d_val[k]) LUXB_CUDA(cudaIpcGetMemHandle(&b.val[k], g->d_val[k]));
+  memcpy(blob, &b, sizeof(b));
+  *blob_bytes = sizeof(P2PBlob);
+  return 0;
+}
+
+int luxb_p2p_import(luxb_graph* g, const void* all_blobs, size_t blob_bytes_each) {
+  LUXB_ARG(g && all_blobs, "NULL argument");
+  LUXB_ARG(blob_bytes_each == sizeof(P2PBlob), "blob size mismatch");
+  if (!g->inited) { set_error("luxb_p2p_import: call luxb_init first"); return LUXB_ERR_STATE; }
+  if (g->P == 1) return 0;
+  LUXB_ARG(g->comm != nullptr, "P2P exchange still needs the communicator for its iteration barrier");
+  LUXB_CUDA(cudaSetDevice(g->cfg.device));
+  const P2PBlob* blobs = reinterpret_cast<const P2PBlob*>(all_blobs);
+  for (int p = 0; p < g->P; ++p) {
+    if (p == g->cfg.rank) { g->peer_val[0][p] = g->d_val[0]; g->peer_val[1][p] = g->d_val[1]; continue; }
+    for (int k = 0; k < 2; ++k) {
+      if (!g->d_val[k]) continue;
+      LUXB_CUDA(cudaIpcOpenMemHandle(&g->peer_val[k][p], blobs[p].val[k], cudaIpcMemLazyEnablePeerAccess));
+    }
+  }
+  g->p2p_ready = true;
+  return 0;
+}
+
+// ---- init ---------------------------------------------------------------------------------------------------
+static int build_push_csr(luxb_graph* g) {
+  // CSR-by-source over this partition's own edges (init_push_* kernels, components_gpu.cu:550-607):
+  // stable radix sort of (src, dst) pairs by src keeps each source's destinations ascending -> deterministic.
+  LUXB_TRY(dmalloc(&g->d_out_end, g->nv));
+  LUXB_TRY(dmalloc(&g->d_out_dst, g->e_part));
+  uint32_t* d_cnt = nullptr;
+  LUXB_TRY(dmalloc(&d_cnt, g->nv));
+  LUXB_CUDA(cudaMemsetAsync(d_cnt, 0, (size_t)g->nv * 4, g->stream));
+  const int grid = g->num_sms * 8;
+  hist_src_kernel<<<grid, 256, 0, g->stream>>>(g->d_src, g->e_part, d_cnt);
+  widen_u32_to_u64_kernel<<<grid, 256, 0, g->stream>>>(d_cnt, g->d_out_end, g->nv);
+  size_t tmp_bytes = 0;
+  LUXB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, g->d_out_end, g->d_out_end, (int)g->nv, g->stream));
+  void* d_tmp = nullptr;
+  LUXB_CUDA(cudaMalloc(&d_tmp, tmp_bytes + 256));
+  LUXB_CUDA(cub::DeviceScan::InclusiveSum(d_tmp, tmp_bytes, g->d_out_end, g->d_out_end, (int)g->nv, g->stream));
+  LUXB_CUDA(cudaStreamSynchronize(g->stream));
+  LUXB_CUDA(cudaFree(d_tmp));
+  LUXB_CUDA(cudaFree(d_cnt));
+  if (g->e_part == 0) return 0;
+  uint32_t *d_dst = nullptr, *d_keys_out = nullptr;
+  LUXB_TRY(dmalloc(&d_dst, g->e_part));
+  LUXB_TRY(dmalloc(&d_keys_out, g->e_part));
+  edge_dst_kernel<<<grid, 256, 0, g->stream>>>(g->d_row_end, g->n_part, g->e_part, g->row_left, d_dst);
+  LUXB_CUDA(cudaGetLastError());
+  int vbits = 1;
+  while ((1ull << vbits) < (uint64_t)g->nv) ++vbits;
+  tmp_bytes = 0;
+  LUXB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, g->d_src, d_keys_out, d_dst, g->d_out_dst, (long long)g->e_part, 0,
+                                            vbits, g->stream));
+  LUXB_CUDA(cudaMalloc(&d_tmp, tmp_bytes + 256));
+  LUXB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, g->d_src, d_keys_out, d_dst, g->d_out_dst, (long long)g->e_part, 0,
+                                            vbits, g->stream));
+  LUXB_CUDA(cudaStreamSynchronize(g->stream));
+  LUXB_CUDA(cudaFree(d_tmp));
+  LUXB_CUDA(cudaFree(d_dst));
+  LUXB_CUDA(cudaFree(d_keys_out));
+  return 0;
+}
+
+static unsigned char* slot_ptr(unsigned char* base, const luxb_graph* g, int p) { return base + g->slot_off[p]; }
+
+// initial labels + frontier (components_gpu.cu:733-739; sssp_gpu.cu:733-744) — every rank builds all slots locally
+static int reset_label_state(luxb_graph* g, bool all_active) {
+  const bool cc = g->cfg.app == LUXB_CC;
+  uint32_t* lab = reinterpret_cast<uint32_t*>(g->d_val[0]);
+  LUXB_CUDA(cudaMemsetAsync(g->d_fq_all, 0, g->fq_total, g->stream));
+  for (int p = 0; p < g->P; ++p) {
+    FrontierHeader h;
+    unsigned char* slot = slot_ptr(g->d_fq_all, g, p);
+    if (cc || all_active) {
+      h.type = LUXB_DENSE_BITMAP;
+      h.num_nodes = g->np[p];
+      uint64_t bytes = g->np[p] ? (g->np[p] - 1) / 8 + 1 : 0;  // (R-L)/8 + 1, components_gpu.cu:737
+      if (bytes) LUXB_CUDA(cudaMemsetAsync(slot + 8, 0xFF, bytes, g->stream));
+    } else {
+      h.type = LUXB_SPARSE_QUEUE;
+      bool mine = g->np[p] && g->cfg.start_vtx >= g->rl[p] && g->cfg.start_vtx - g->rl[p] < g->np[p];
+      h.num_nodes = mine ? 1 : 0;
+      if (mine) {
+        uint32_t q[1] = {g->cfg.start_vtx};
+        uint32_t zero[1] = {0};
+        LUXB_CUDA(cudaMemcpyAsync(slot + 8, q, 4, cudaMemcpyHostToDevice, g->stream));
+        LUXB_CUDA(cudaMemcpyAsync(slot + 8 + (size_t)g->cap[p] * 4, zero, 4, cudaMemcpyHostToDevice, g->stream));
+      }
+    }
+    LUXB_CUDA(cudaMemcpyAsync(slot, &h, 8, cudaMemcpyHostToDevice, g->stream));
+    g->h_hdr[2 * p] = h.type;
+    g->h_hdr[2 * p + 1] = h.num_nodes;
+  }
+  if (!all_active) {
+    const int grid = g->num_sms * 8;
+    if (cc) iota_kernel<<<grid, 256, 0, g->stream>>>(lab, g->nv);
+    else {
+      fill_kernel<uint32_t><<<grid, 256, 0, g->stream>>>(lab, g->nv, g->nv);
+      uint32_t zero = 0;
+      if (g->cfg.start_vtx < g->nv)
+        LUXB_CUDA(cudaMemcpyAsync(lab + g->cfg.start_vtx, &zero, 4, cudaMemcpyHostToDevice, g->stream));
+    }
+    LUXB_CUDA(cudaGetLastError());
+  }
+  if (g->n_part)
+    LUXB_CUDA(cudaMemcpyAsync(g->d_cur, lab + g->row_left, (size_t)g->n_part * 4, cudaMemcpyDeviceToDevice, g->stream));
+  LUXB_CUDA(cudaStreamSynchronize(g->stream));
+  g->stats.last_active = 0;
+  for (int p = 0; p < g->P; ++p) g->stats.last_active += g->h_hdr[2 * p + 1];
+  g->stats.last_frontier_type = g->h_hdr[2 * g->cfg.rank];
+  return 0;
+}
+
+int luxb_init(luxb_graph* g) {
+  LUXB_ARG(g != nullptr, "graph is NULL");
+  if (g->inited) { set_error("luxb_init called twice"); return LUXB_ERR_STATE; }
+  if (g->P > 1 && !g->comm) { set_error("luxb_init: nranks > 1 needs luxb_comm_init first"); return LUXB_ERR_STATE; }
+  LUXB_CUDA(cudaSetDevice(g->cfg.device));
+  const int grid = g->num_sms * 8;
+  switch (g->cfg.app) {
+    case LUXB_PAGERANK: {
+      g->vbytes = 4;
+      LUXB_TRY(dmalloc(&g->d_deg, g->nv));
+      LUXB_CUDA(cudaMemsetAsync(g->d_deg, 0, (size_t)g->nv * 4, g->stream));
+      hist_src_kernel<<<grid, 256, 0, g->stream>>>(g->d_src, g->e_part, g->d_deg);  // pull_scan_task_impl
+      LUXB_CUDA(cudaGetLastError());
+      if (g->P > 1) LUXB_NCCL(nccl().AllReduce(g->d_deg, g->d_deg, g->nv, ncclUint32, ncclSum, g->comm, g->stream));
+      for (int k = 0; k < 2; ++k) LUXB_TRY(dmalloc((float**)&g->d_val[k], g->nv));
+      pr_init_kernel<<<grid, 256, 0, g->stream>>>(g->d_deg, g->nv, (float*)g->d_val[0]);
+      LUXB_CUDA(cudaMemsetAsync(g->d_val[1], 0, (size_t)g->nv * 4, g->stream));
+      LUXB_CUDA(cudaGetLastError());
+      break;
+    }
+    case LUXB_COLFILTER: {
+      g->vbytes = 4 * kCfK;
+      for (int k = 0; k < 2; ++k) LUXB_TRY(dmalloc((float**)&g->d_val[k], (uint64_t)g->nv * kCfK));
+      cf_init_kernel<<<grid, 256, 0, g->stream>>>((float*)g->d_val[0], (uint64_t)g->nv * kCfK);
+      cf_init_kernel<<<grid, 256, 0, g->stream>>>((float*)g->d_val[1], (uint64_t)g->nv * kCfK);
+      // chunk table
+      uint32_t* d_cnt = nullptr;
+      LUXB_TRY(dmalloc(&d_cnt, (uint64_t)g->n_part + 1));
+      LUXB_TRY(dmalloc(&g->d_chunk_first, (uint64_t)g->n_part + 2));
+      LUXB_CUDA(cudaMemsetAsync(d_cnt, 0, ((size_t)g->n_part + 1) * 4, g->stream));
+      cf_chunk_count_kernel<<<grid, 256, 0, g->stream>>>(g->d_row_end, g->n_part, d_cnt);
+      size_t tmp_bytes = 0;
+      LUXB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_cnt, g->d_chunk_first, (int)g->n_part + 1, g->stream));
+      void* d_tmp = nullptr;
+      LUXB_CUDA(cudaMalloc(&d_tmp, tmp_bytes + 256));
+      LUXB_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_cnt, g->d_chunk_first, (int)g->n_part + 1, g->stream));
+      LUXB_CUDA(cudaMemcpyAsync(&g->n_chunks, g->d_chunk_first + g->n_part, 4, cudaMemcpyDeviceToHost, g->stream));
+      LUXB_CUDA(cudaStreamSynchronize(g->stream));
+      LUXB_CUDA(cudaFree(d_tmp));
+      LUXB_CUDA(cudaFree(d_cnt));
+      LUXB_TRY(dmalloc(&g->d_chunk_vtx, g->n_chunks));
+      LUXB_TRY(dmalloc(&g->d_partial, (uint64_t)g->n_chunks * kCfK));
+      cf_chunk_fill_kernel<<<grid, 256, 0, g->stream>>>(g->d_chunk_first, g->n_part, g->d_chunk_vtx);
+      LUXB_CUDA(cudaGetLastError());
+      break;
+    }
+    case LUXB_CC:
+    case LUXB_SSSP: {
+      g->vbytes = 4;
+      LUXB_ARG(g->cfg.app != LUXB_SSSP || g->cfg.start_vtx < g->nv, "start vertex %u >= nv", g->cfg.start_vtx);
+      LUXB_TRY(dmalloc((uint32_t**)&g->d_val[0], g->nv));
+      LUXB_TRY(dmalloc(&g->d_cur, g->n_part));
+      LUXB_TRY(build_push_csr(g));
+      LUXB_TRY(dmalloc(&g->d_fq_all, g->fq_total));
+      LUXB_TRY(dmalloc(&g->d_fq_new, g->slot_bytes[g->cfg.rank]));
+      LUXB_TRY(dmalloc(&g->d_fq_tmp, g->slot_bytes[g->cfg.rank]));
+      LUXB_TRY(dmalloc(&g->d_hdr_all, 2 * LUXB_MAX_PARTS));
+      LUXB_CUDA(cudaMallocHost(&g->h_hdr, 2 * LUXB_MAX_PARTS * 4));
+      LUXB_CUDA(cudaMallocHost(&g->h_scratch, 64));
+      LUXB_TRY(reset_label_state(g, false));
+      break;
+    }
+  }
+  LUXB_CUDA(cudaStreamSynchronize(g->stream));
+  g->cur = 0;
+  g->inited = true;
+  return 0;
+}
+
+// ---- exchange helpers ---------------------------------------------------------------------------------------
+// all-gather of unequal slices = one grouped set of in-place broadcasts (root p sends partition p's slice)
+static int allgather_slices(luxb_graph* g, void* replica, size_t elem_bytes) {
+  if (g->P == 1) return 0;
+  LUXB_NCCL(nccl().GroupStart());
+  for (int p = 0; p < g->P; ++p) {
+    if (g->np[p] == 0) continue;
+    char* ptr = reinterpret_cast<char*>(replica) + (size_t)g->rl[p] * elem_bytes;
+    LUXB_NCCL(nccl().Broadcast(ptr, ptr, (size_t)g->np[p] * elem_bytes, ncclUint8, p, g->comm, g->stream));
+  }
+  LUXB_NCCL(nccl().GroupEnd());
+  return 0;
+}
+
+// iteration barrier of the P2P exchange: a 4-byte all-reduce enqueued after the compute kernels; when it
+// completes on a rank, every peer's kernels (and therefore their stores into this rank's replica) are done.
+static int p2p_barrier(luxb_graph* g) {
+  if (g->P == 1) return 0;
+  if (!g->d_sync) LUXB_TRY(dmalloc(&g->d_sync, 4));
+  LUXB_NCCL(nccl().AllReduce(g->d_sync, g->d_sync, 1, ncclUint32, ncclSum, g->comm, g->stream));
+  return 0;
+}
+
+extern "C++" {
+template <class Prog>
+static int launch_pull(luxb_graph* g, const typename Prog::Vertex* x_old, typename Prog::Vertex* out_local,
+                       const typename Prog::Params& prm, int out_replica /* -1: no peers */) {
+  using Shape = PullShapeDefault;
+  if (g->n_tiles == 0) return 0;
+  PullArgs<Prog> a{};
+  a.row_end = g->d_row_end;
+  a.src = g->d_src;
+  a.tile_v = g->d_tile_v;
+  a.n_part = g->n_part;
+  a.e_part = g->e_part;
+  a.n_tiles = g->n_tiles;
+  a.row_left = g->row_left;
+  a.x_old = x_old;
+  a.out = out_local;
+  a.head_partial = reinterpret_cast<typename Prog::Acc*>(g->d_head);
+  a.tail_partial = reinterpret_cast<typename Prog::Acc*>(g->d_tail);
+  a.prm = prm;
+  a.n_peers = 0;
+  if (out_replica >= 0 && g->p2p_ready && g->cfg.exchange == LUXB_EXCHANGE_P2P) {
+    for (int p = 0; p < g->P; ++p) {
+      if (p == g->cfg.rank) continue;
+      a.peer_out[a.n_peers++] = reinterpret_cast<typename Prog::Vertex*>(g->peer_val[out_replica][p]) + g->row_left;
+    }
+  }
+  static bool attr_set = false;
+  auto kern = pull_tile_kernel<Prog, Shape>;
+  if (!attr_set) {
+    LUXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Shape::kSmemBytes));
+    attr_set = true;
+  }
+  int occ = 0;
+  LUXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Shape::kThreads, Shape::kSmemBytes));
+  if (occ < 1) occ = 1;
+  uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)g->num_sms * occ, g->n_tiles);
+  kern<<<grid, Shape::kThreads, Shape::kSmemBytes, g->stream>>>(a);
+  LUXB_CUDA(cudaGetLastError());
+  g->stats.kernel_launches++;
+  if (g->n_tiles > 1) {
+    pull_fixup_kernel<Prog><<<(g->n_tiles - 1 + 255) / 256, 256, 0, g->stream>>>(a);
+    LUXB_CUDA(cudaGetLastError());
+    g->stats.kernel_launches++;
+  }
+  return 0;
+}
+
+}  // extern "C++"
+
+static int pagerank_iteration(luxb_graph* g) {
+  PageRankProgram::Params prm;
+  prm.init_rank = (1.0f - kAlpha) / (float)g->nv;  // pagerank_gpu.cu:144
+  prm.deg = g->d_deg;
+  float* x_old = (float*)g->d_val[g->cur];
+  float* x_new = (float*)g->d_val[1 - g->cur];
+  LUXB_TRY(launch_pull<PageRankProgram>(g, x_old, x_new + g->row_left, prm, 1 - g->cur));
+  if (g->P > 1) {
+    if (g->p2p_ready && g->cfg.exchange == LUXB_EXCHANGE_P2P) LUXB_TRY(p2p_barrier(g));
+    else LUXB_TRY(allgather_slices(g, x_new, 4));
+  }
+  g->cur ^= 1;
+  g->stats.edges_processed += g->e_part;
+  return 0;
+}
+
+static int colfilter_iteration(luxb_graph* g) {
+  float* x_old = (float*)g->d_val[g->cur];
+  float* x_new = (float*)g->d_val[1 - g->cur];
+  if (g->n_part) {
+    CfArgs a{};
+    a.row_end = g->d_row_end;
+    a.src = g->d_src;
+    a.weight = g->d_weight;
+    a.chunk_first = g->d_chunk_first;
+    a.chunk_vtx = g->d_chunk_vtx;
+    a.n_part = g->n_part;
+    a.n_chunks = g->n_chunks;
+    a.row_left = g->row_left;
+    a.x_old = x_old;
+    a.partial = g->d_partial;
+    a.out = x_new + (size_t)g->row_left * kCfK;
+    a.n_peers = 0;
+    if (g->p2p_ready && g->cfg.exchange == LUXB_EXCHANGE_P2P)
+      for (int p = 0; p < g->P; ++p)
+        if (p != g->cfg.rank) a.peer_out[a.n_peers++] = (float*)g->peer_val[1 - g->cur][p] + (size_t)g->row_left * kCfK;
+    uint64_t warps = g->n_chunks;
+    int grid = (int)std::min<uint64_t>((warps * 32 + 255) / 256, (uint64_t)g->num_sms * 8);
+    cf_chunk_kernel<<<grid, 256, 0, g->stream>>>(a);
+    cf_update_kernel<<<grid_for((uint64_t)g->n_part * kCfK, 256, g->num_sms * 8), 256, 0, g->stream>>>(a);
+    LUXB_CUDA(cudaGetLastError());
+    g->stats.kernel_launches += 2;
+  }
+  if (g->P > 1) {
+    if (g->p2p_ready && g->cfg.exchange == LUXB_EXCHANGE_P2P) LUXB_TRY(p2p_barrier(g));
+    else LUXB_TRY(allgather_slices(g, x_new, 4 * kCfK));
+  }
+  g->cur ^= 1;
+  g->stats.edges_processed += g->e_part;
+  return 0;
+}
+
+// one PushAppTask (push_app_task_impl, components_gpu.cu:335-522) on this rank, including the exchange
+extern "C++" {
+template <class Prog>
+static int label_iteration(luxb_graph* g) {
+  const int me = g->cfg.rank;
+  uint32_t* lab = reinterpret_cast<uint32_t*>(g->d_val[0]);
+  // direction + representation decisions from the gathered headers (components_gpu.cu:397-416)
+  uint64_t old_size = 0;
+  int dense_parts = 0, sparse_parts = 0;
+  for (int p = 0; p < g->P; ++p) {
+    old_size += g->h_hdr[2 * p + 1];
+    if (g->h_hdr[2 * p] == LUXB_DENSE_BITMAP) dense_parts++; else sparse_parts++;
+  }
+  bool dense_fq = dense_parts >= sparse_parts;
+  const bool pull = old_size > (uint64_t)(g->nv / 16);
+  if (pull) dense_fq = true;
+  const uint32_t max_nodes = g->cap[me];
+  unsigned char* new_slot = g->d_fq_new;
+  LUXB_CUDA(cudaMemsetAsync(new_slot, 0, 8, g->stream));  // components_gpu.cu:412
+
+  if (pull) {
+    typename Prog::Params prm{0};
+    LUXB_TRY(launch_pull<Prog>(g, lab, g->d_cur, prm, -1));
+    g->stats.edges_processed += g->e_part;
+    g->stats.pull_iterations++;
+  } else if (g->n_part && old_size) {
+    PushArgs a{};
+    uint64_t blocks = 0;
+    for (int p = 0; p < g->P; ++p) {
+      a.fr[p].slot = slot_ptr(g->d_fq_all, g, p);
+      a.fr[p].row_left = g->rl[p];
+      a.fr[p].n_part = g->np[p];
+      a.fr[p].type = g->h_hdr[2 * p];
+      a.fr[p].count = std::min(g->h_hdr[2 * p + 1], g->cap[p]);
+      uint32_t entries = a.fr[p].type == LUXB_DENSE_BITMAP ? (g->h_hdr[2 * p + 1] ? g->np[p] : 0) : a.fr[p].count;
+      if (a.fr[p].type == LUXB_DENSE_BITMAP && g->h_hdr[2 * p + 1] == 0) a.fr[p].n_part = 0;
+      blocks += (entries + kPushThreads - 1) / kPushThreads;
+    }
+    a.n_parts = g->P;
+    a.out_end = g->d_out_end;
+    a.out_dst = g->d_out_dst;
+    a.lab = lab;
+    a.cur = g->d_cur;
+    a.row_left = g->row_left;
+    a.new_sparse = dense_fq ? 0 : 1;
+    a.new_count = reinterpret_cast<uint32_t*>(new_slot) + 1;
+    a.new_queue = reinterpret_cast<uint32_t*>(new_slot + 8);
+    a.max_nodes = max_nodes;
+    a.edges_scanned = g->d_counters;
+    if (blocks) {
+      push_relax_kernel<Prog><<<(unsigned)blocks, kPushThreads, 0, g->stream>>>(a);
+      LUXB_CUDA(cudaGetLastError());
+      g->stats.kernel_launches++;
+    }
+  }
+
+  // ---- new frontier of this partition (components_gpu.cu:462-491) ----
+  const int fgrid = grid_for(g->n_part, 256, g->num_sms * 8);
+  uint32_t count = 0;
+  if (dense_fq) {
+    if (g->n_part) {
+      frontier_diff_kernel<<<fgrid, 256, 0, g->stream>>>(lab + g->row_left, g->d_cur, g->n_part, new_slot);
+      g->stats.kernel_launches++;
+    }
+    LUXB_CUDA(cudaMemcpyAsync(g->h_scratch, new_slot, 8, cudaMemcpyDeviceToHost, g->stream));
+    LUXB_CUDA(cudaStreamSynchronize(g->stream));
+    count = g->h_scratch[1];
+    if (count < max_nodes) {  // demote to a queue
+      LUXB_CUDA(cudaMemsetAsync(g->d_fq_tmp, 0, 8, g->stream));
+      if (count) {
+        frontier_d2s_kernel<<<fgrid, 256, 0, g->stream>>>(new_slot, g->row_left, g->n_part, g->d_fq_tmp, max_nodes);
+        g->stats.kernel_launches++;
+      }
+      std::swap(g->d_fq_new, g->d_fq_tmp);
+      new_slot = g->d_fq_new;
+      dense_fq = false;
+    }
+  } else {
+    LUXB_CUDA(cudaMemcpyAsync(g->h_scratch, new_slot, 8, cudaMemcpyDeviceToHost, g->stream));
+    LUXB_CUDA(cudaStreamSynchronize(g->stream));
+    count = g->h_scratch[1];
+    if (count >= max_nodes) {  // promote: rebuild as a bitmap from the label diff (count is re-derived exactly)
+      dense_fq = true;
+      LUXB_CUDA(cudaMemsetAsync(new_slot, 0, 8, g->stream));
+      frontier_diff_kernel<<<fgrid, 256, 0, g->stream>>>(lab + g->row_left, g->d_cur, g->n_part, new_slot);
+      g->stats.kernel_launches++;
+      LUXB_CUDA(cudaMemcpyAsync(g->h_scratch, new_slot, 8, cudaMemcpyDeviceToHost, g->stream));
+      LUXB_CUDA(cudaStreamSynchronize(g->stream));
+      count = g->h_scratch[1];
+    }
+  }
+  FrontierHeader my_hdr{dense_fq ? LUXB_DENSE_BITMAP : LUXB_SPARSE_QUEUE, count};
+  LUXB_CUDA(cudaMemcpyAsync(new_slot, &my_hdr, 8, cudaMemcpyHostToDevice, g->stream));
+  if (!dense_fq && count) {
+    frontier_pack_labels_kernel<<<grid_for(count, 256, g->num_sms * 4), 256, 0, g->stream>>>(new_slot, max_nodes, g->row_left,
+                                                                                            g->d_cur);
+    g->stats.kernel_launches++;
+  }
+  LUXB_CUDA(cudaGetLastError());
+
+  // ---- exchange: headers, then payload sized by each partition's representation ----
+  if (g->P > 1) {
+    LUXB_NCCL(nccl().AllGather(new_slot, g->d_hdr_all, 8, ncclUint8, g->comm, g->stream));
+    LUXB_CUDA(cudaMemcpyAsync(g->h_hdr, g->d_hdr_all, (size_t)g->P * 8, cudaMemcpyDeviceToHost, g->stream));
+    LUXB_CUDA(cudaStreamSynchronize(g->stream));
+  } else {
+    g->h_hdr[0] = my_hdr.type;
+    g->h_hdr[1] = my_hdr.num_nodes;
+  }
+  uint64_t total = 0;
+  for (int p = 0; p < g->P; ++p) total += g->h_hdr[2 * p + 1];
+  if (g->P > 1) {
+    LUXB_NCCL(nccl().GroupStart());
+    for (int p = 0; p < g->P; ++p) {
+      uint32_t type = g->h_hdr[2 * p], cnt = g->h_hdr[2 * p + 1];
+      unsigned char* dst_slot = slot_ptr(g->d_fq_all, g, p);
+      const unsigned char* send_slot = p == me ? new_slot : dst_slot;
+      LUXB_NCCL(nccl().Broadcast(send_slot, dst_slot, 8, ncclUint8, p, g->comm, g->stream));
+      if (cnt == 0 || g->np[p] == 0) continue;
+      if (type == LUXB_DENSE_BITMAP) {
+        size_t bm_bytes = (((size_t)g->np[p] + 31) / 32) * 4;
+        LUXB_NCCL(nccl().Broadcast(send_slot + 8, dst_slot + 8, bm_bytes, ncclUint8, p, g->comm, g->stream));
+        const void* send_lab = p == me ? (const void*)g->d_cur : (const void*)(lab + g->rl[p]);
+        LUXB_NCCL(nccl().Broadcast(send_lab, lab + g->rl[p], (size_t)g->np[p] * 4, ncclUint8, p, g->comm, g->stream));
+      } else {
+        size_t qoff = 8 + (size_t)g->cap[p] * 4;
+        LUXB_NCCL(nccl().Broadcast(send_slot + 8, dst_slot + 8, (size_t)cnt * 4, ncclUint8, p, g->comm, g->stream));
+        LUXB_NCCL(nccl().Broadcast(send_slot + qoff, dst_slot + qoff, (size_t)cnt * 4, ncclUint8, p, g->comm, g->stream));
+      }
+    }
+    LUXB_NCCL(nccl().GroupEnd());
+  } else {
+    LUXB_CUDA(cudaMemcpyAsync(g->d_fq_all, new_slot, g->slot_bytes[0], cudaMemcpyDeviceToDevice, g->stream));
+    if (dense_fq && count && g->n_part)
+      LUXB_CUDA(cudaMemcpyAsync(lab + g->row_left, g->d_cur, (size_t)g->n_part * 4, cudaMemcpyDeviceToDevice, g->stream));
+  }
+  for (int p = 0; p < g->P; ++p) {
+    uint32_t type = g->h_hdr[2 * p], cnt = g->h_hdr[2 * p + 1];
+    if (type == LUXB_SPARSE_QUEUE && cnt) {
+      frontier_apply_kernel<<<grid_for(cnt, 256, g->num_sms * 4), 256, 0, g->stream>>>(slot_ptr(g->d_fq_all, g, p), g->cap[p], cnt, lab);
+      g->stats.kernel_launches++;
+    }
+  }
+  LUXB_CUDA(cudaGetLastError());
+  g->stats.last_active = total;
+  g->stats.last_frontier_type = my_hdr.type;
+  g->trace_active.push_back(total);
+  g->trace_pull.push_back(pull ? 1 : 0);
+  if (g->cfg.verbose)
+    printf("rowLeft(%u) activeNodes(%u) globalActive(%llu) %s\n", g->row_left, count, (unsigned long long)total, pull ? "pull" : "push");
+  return 0;
+}
+
+}  // extern "C++"
+
+static int one_iteration(luxb_graph* g) {
+  switch (g->cfg.app) {
+    case LUXB_PAGERANK: return pagerank_iteration(g);
+    case LUXB_COLFILTER: return colfilter_iteration(g);
+    case LUXB_CC: return label_iteration<MaxLabelProgram>(g);
+    case LUXB_SSSP: return label_iteration<HopDistProgram>(g);
+  }
+  return LUXB_ERR_ARG;
+}
+
+static int finish_timed(luxb_graph* g) {
+  LUXB_CUDA(cudaEventRecord(g->ev_end, g->stream));
+  LUXB_CUDA(cudaStreamSynchronize(g->stream));
+  float ms = 0.f;
+  LUXB_CUDA(cudaEventElapsedTime(&ms, g->ev_begin, g->ev_end));
+  g->stats.loop_seconds += ms * 1e-3;
+  if (g->d_out_end) {
+    unsigned long long scanned = 0;
+    LUXB_CUDA(cudaMemcpy(&scanned, g->d_counters, 8, cudaMemcpyDeviceToHost));
+    LUXB_CUDA(cudaMemset(g->d_counters, 0, 8));
+    g->stats.edges_processed += scanned;
+  }
+  return 0;
+}
+
+int luxb_iterate(luxb_graph* g, int iters, uint64_t* active_out) {
+  LUXB_ARG(g != nullptr, "graph is NULL");
+  if (!g->inited) { set_error("luxb_iterate before luxb_init"); return LUXB_ERR_STATE; }
+  LUXB_ARG(iters >= 0, "negative iteration count");
+  LUXB_CUDA(cudaSetDevice(g->cfg.device));
+  LUXB_CUDA(cudaEventRecord(g->ev_begin, g->stream));
+  for (int i = 0; i < iters; ++i) {
+    LUXB_TRY(one_iteration(g));
+    g->stats.iterations++;
+  }
+  LUXB_TRY(finish_timed(g));
+  if (active_out) *active_out = g->stats.last_active;
+  return 0;
+}
+
+int luxb_run_to_convergence(luxb_graph* g, int max_iters, int* iters_out) {
+  LUXB_ARG(g != nullptr, "graph is NULL");
+  if (!g->inited) { set_error("luxb_run_to_convergence before luxb_init"); return LUXB_ERR_STATE; }
+  LUXB_ARG(g->cfg.app == LUXB_CC || g->cfg.app == LUXB_SSSP, "only push apps converge (pagerank/col_filter run -ni iterations)");
+  LUXB_CUDA(cudaSetDevice(g->cfg.device));
+  LUXB_CUDA(cudaEventRecord(g->ev_begin, g->stream));
+  int it = 0;
+  while (max_iters <= 0 || it < max_iters) {
+    LUXB_TRY(one_iteration(g));
+    g->stats.iterations++;
+    ++it;
+    if (g->stats.last_active == 0) break;  // components.cc:116-123 without the 4-deep window
+  }
+  LUXB_TRY(finish_timed(g));
+  if (iters_out) *iters_out = it;
+  return 0;
+}
+
+int luxb_get_values(luxb_graph* g, void* host_out, size_t bytes) {
+  LUXB_ARG(g && host_out, "NULL argument");
+  if (!g->inited) { set_error("luxb_get_values before luxb_init"); return LUXB_ERR_STATE; }
+  size_t need = (size_t)g->nv * g->vbytes;
+  LUXB_ARG(bytes == need, "buffer is %zu bytes, vertex values need %zu", bytes, need);
+  LUXB_CUDA(cudaSetDevice(g->cfg.device));
+  const void* srcp = (g->cfg.app == LUXB_CC || g->cfg.app == LUXB_SSSP) ? g->d_val[0] : g->d_val[g->cur];
+  LUXB_CUDA(cudaMemcpyAsync(host_out, srcp, need, cudaMemcpyDeviceToHost, g->stream));
+  LUXB_CUDA(cudaStreamSynchronize(g->stream));
+  return 0;
+}
+
+int luxb_set_values(luxb_graph* g, const void* host_in, size_t bytes) {
+  LUXB_ARG(g && host_in, "NULL argument");
+  if (!g->inited) { set_error("luxb_set_values before luxb_init"); return LUXB_ERR_STATE; }
+  size_t need = (size_t)g->nv * g->vbytes;
+  LUXB_ARG(bytes == need, "buffer is %zu bytes, vertex values need %zu", bytes, need);
+  LUXB_CUDA(cudaSetDevice(g->cfg.device));
+  const bool labels = g->cfg.app == LUXB_CC || g->cfg.app == LUXB_SSSP;
+  void* dstp = labels ? g->d_val[0] : g->d_val[g->cur];
+  LUXB_CUDA(cudaMemcpyAsync(dstp, host_in, need, cudaMemcpyHostToDevice, g->stream));
+  if (labels) LUXB_TRY(reset_label_state(g, true));
+  LUXB_CUDA(cudaStreamSynchronize(g->stream));
+  return 0;
+}
+
+int luxb_check(luxb_graph* g, uint64_t* mistakes_out) {
+  LUXB_ARG(g && mistakes_out, "NULL argument");
+  if (!g->inited) { set_error("luxb_check before luxb_init"); return LUXB_ERR_STATE; }
+  LUXB_ARG(g->cfg.app == LUXB_CC || g->cfg.app == LUXB_SSSP,
+           "the reference has no check for pagerank / col_filter (CHECK_TASK_ID is not registered in pull_model.inl:482-521)");
+  LUXB_CUDA(cudaSetDevice(g->cfg.device));
+  LUXB_CUDA(cudaMemsetAsync(g->d_counters + 1, 0, 8, g->stream));
+  const uint32_t* lab = reinterpret_cast<const uint32_t*>(g->d_val[0]);
+  int grid = grid_for(g->n_part, 256, g->num_sms * 8);
+  if (g->n_part) {
+    if (g->cfg.app == LUXB_CC)
+      check_kernel<MaxLabelProgram><<<grid, 256, 0, g->stream>>>(g->d_row_end, g->d_src, g->n_part, g->row_left, g->nv, lab, g->d_counters + 1);
+    else
+      check_kernel<HopDistProgram><<<grid, 256, 0, g->stream>>>(g->d_row_end, g->d_src, g->n_part, g->row_left, g->nv, lab, g->d_counters + 1);
+    LUXB_CUDA(cudaGetLastError());
+  }
+  unsigned long long bad = 0;
+  LUXB_CUDA(cudaMemcpyAsync(&bad, g->d_counters + 1, 8, cudaMemcpyDeviceToHost, g->stream));
+  LUXB_CUDA(cudaStreamSynchronize(g->stream));
+  *mistakes_out = bad;
+  return 0;
+}
+
+int luxb_stats(const luxb_graph* g, luxb_stats_t* out) {
+  LUXB_ARG(g && out, "NULL argument");
+  *out = g->stats;
+  return 0;
+}
+
+int luxb_trace(const luxb_graph* g, uint64_t* active, int32_t* pull, int max_entries) {
+  LUXB_ARG(g != nullptr, "graph is NULL");
+  int n = (int)std::min<size_t>(g->trace_active.size(), (size_t)std::max(max_entries, 0));
+  for (int i = 0; i < n; ++i) {
+    if (active) active[i] = g->trace_active[i];
+    if (pull) pull[i] = g->trace_pull[i];
+  }
+  return n;
+}
+
+int luxb_device_view_get(luxb_graph* g, luxb_device_view* out) {
+  LUXB_ARG(g && out, "NULL argument");
+  const bool labels = g->cfg.app == LUXB_CC || g->cfg.app == LUXB_SSSP;
+  out->values = g->inited ? (labels ? g->d_val[0] : g->d_val[g->cur]) : nullptr;
+  out->row_end = g->d_row_end;
+  out->src = g->d_src;
+  out->stream = g->stream;
+  out->row_left = g->row_left;
+  out->row_right = g->row_left + g->n_part - 1;
+  out->local_edges = g->e_part;
+  return 0;
+}
+
+int luxb_get_local_csc(luxb_graph* g, luxb_eid* row_end_abs, luxb_vid* src, int32_t* weight) {
+  LUXB_ARG(g != nullptr, "graph is NULL");
+  LUXB_CUDA(cudaSetDevice(g->cfg.device));
+  if (row_end_abs && g->n_part) {
+    LUXB_CUDA(cudaMemcpy(row_end_abs, g->d_row_end, (size_t)g->n_part * 8, cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < g->n_part; ++i) row_end_abs[i] += g->col_left;
+  }
+  if (src && g->e_part) LUXB_CUDA(cudaMemcpy(src, g->d_src, g->e_part * 4, cudaMemcpyDeviceToHost));
+  if (weight) {
+    LUXB_ARG(g->d_weight != nullptr, "graph has no weights");
+    if (g->e_part) LUXB_CUDA(cudaMemcpy(weight, g->d_weight, g->e_part * 4, cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
+void luxb_close(luxb_graph* g) {
+  if (!g) return;
+  cudaSetDevice(g->cfg.device);
+  if (g->stream) cudaStreamSynchronize(g->stream);
+  if (g->p2p_ready)
+    for (int p = 0; p < g->P; ++p)
+      if (p != g->cfg.rank)
+        for (int k = 0; k < 2; ++k)
+          if (g->peer_val[k][p]) cudaIpcCloseMemHandle(g->peer_val[k][p]);
+  if (g->comm) nccl().CommDestroy(g->comm);
+  void* ptrs[] = {g->d_row_end, g->d_src, g->d_weight, g->d_tile_v, g->d_head, g->d_tail, g->d_deg, g->d_val[0], g->d_val[1],
+                  g->d_cur, g->d_out_end, g->d_out_dst, g->d_fq_all, g->d_fq_new, g->d_fq_tmp, g->d_hdr_all, g->d_counters,
+                  g->d_chunk_first, g->d_chunk_vtx, g->d_partial, g->d_sync};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (g->h_hdr) cudaFreeHost(g->h_hdr);
+  if (g->h_scratch) cudaFreeHost(g->h_scratch);
+  if (g->ev_begin) cudaEventDestroy(g->ev_begin);
+  if (g->ev_end) cudaEventDestroy(g->ev_end);
+  if (g->stream) cudaStreamDestroy(g->stream);
+  delete g;
+}
+
+}  // extern "C"

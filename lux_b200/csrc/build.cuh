@@ -1,0 +1,205 @@
+// build.cuh — one-time graph construction on the device: synthetic generators, partitioning, per-partition
+// layout (relative row_end with sentinels, padded source ids), out-degrees, CSR-by-source for the push model.
+// Replaces the CPU load/scan tasks and the init kernels of the reference:
+//   pull_scan_task_impl  pull_model.inl:322-345      -> hist_src_kernel
+//   init_push_kernel / init_push_row_ptrs / init_push_col_idxs components_gpu.cu:550-607 -> build_push_csr()
+//   Graph::Graph partitioner pull_model.inl:108-131  -> partition_kernel (bit-identical bounds)
+// Not on the timed hot path; device-wide scans/sorts use CUB (bundled with CUDA, as the reference itself does).
+#pragma once
+#include "common.cuh"
+
+namespace luxb {
+
+// ---- deterministic counter-based generators; MUST match oracle/lux_oracle.c lo_rmat_edge bit for bit ---------
+#define LUXB_RMAT_T0 37356u
+#define LUXB_RMAT_T1 49807u
+#define LUXB_RMAT_T2 62259u
+
+__device__ __forceinline__ void rmat_edge(uint64_t seed_mixed, uint64_t i, int scale, uint32_t nv, uint32_t& src,
+                                          uint32_t& dst) {
+  uint64_t h0 = splitmix64(seed_mixed ^ i);
+  for (uint64_t attempt = 0;; ++attempt) {
+    uint64_t ha = splitmix64(h0 + attempt);
+    uint32_t s = 0, d = 0;
+    uint64_t w = 0;
+    for (int lvl = 0; lvl < scale; ++lvl) {
+      if ((lvl & 3) == 0) w = splitmix64(ha ^ ((uint64_t)(lvl / 4 + 1) * 0xA0761D6478BD642Full));
+      uint32_t r = (uint32_t)(w & 0xFFFFu);
+      w >>= 16;
+      uint32_t sb = r >= LUXB_RMAT_T1 ? 1u : 0u;
+      uint32_t db = (r >= LUXB_RMAT_T0 && r < LUXB_RMAT_T1) || r >= LUXB_RMAT_T2 ? 1u : 0u;
+      s = (s << 1) | sb;
+      d = (d << 1) | db;
+    }
+    if (s < nv && d < nv) { src = s; dst = d; return; }
+  }
+}
+
+__device__ __forceinline__ int32_t edge_weight(uint64_t seed, uint32_t src, uint32_t dst) {
+  uint64_t h = splitmix64(splitmix64(seed ^ 0x5bd1e995u) ^ (((uint64_t)dst << 32) | src));
+  return (int32_t)(1 + (h >> 33) % 5);
+}
+
+__device__ __forceinline__ void bipartite_edge(uint64_t seed_mixed, uint64_t j, uint32_t users, uint32_t items,
+                                               uint32_t& user, uint32_t& item) {
+  uint64_t h1 = splitmix64(seed_mixed ^ j);
+  uint64_t h2 = splitmix64(h1 ^ 0xA0761D6478BD642Full);
+  user = (uint32_t)(((h1 >> 32) * (uint64_t)users) >> 32);
+  uint64_t a = h2 & 0xFFFFFFFFull, b = h2 >> 32;
+  uint64_t m = (a * b) >> 32;
+  item = users + (uint32_t)((m * (uint64_t)items) >> 32);
+}
+
+// kind 0: RMAT (ne edges).  kind 1: bipartite (ne = 2*ratings; edge 2j = user->item, 2j+1 = item->user).
+struct GenSpec {
+  int kind;
+  int scale;
+  uint32_t nv;
+  uint64_t ne;
+  uint64_t seed;
+  uint32_t users, items;
+};
+
+__device__ __forceinline__ void gen_edge(const GenSpec& g, uint64_t seed_mixed, uint64_t e, uint32_t& s, uint32_t& d) {
+  if (g.kind == 0) {
+    rmat_edge(seed_mixed, e, g.scale, g.nv, s, d);
+  } else {
+    uint32_t u, it;
+    bipartite_edge(seed_mixed, e >> 1, g.users, g.items, u, it);
+    if (e & 1) { s = it; d = u; } else { s = u; d = it; }
+  }
+}
+
+__global__ void gen_count_indeg_kernel(GenSpec g, uint32_t* __restrict__ indeg) {
+  uint64_t seed_mixed = splitmix64(g.seed);
+  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < g.ne; e += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t s, d;
+    gen_edge(g, seed_mixed, e, s, d);
+    atomicAdd(indeg + d, 1u);
+  }
+}
+
+// emit key = (dst - row_left) << 32 | src for the edges whose destination lies in [row_left, row_left + n_part)
+__global__ void gen_emit_keys_kernel(GenSpec g, uint32_t row_left, uint32_t n_part, unsigned long long* cursor,
+                                     uint64_t* __restrict__ keys, uint64_t capacity) {
+  uint64_t seed_mixed = splitmix64(g.seed);
+  const unsigned lane = threadIdx.x & 31;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t rounds = (g.ne + stride - 1) / stride;
+  for (uint64_t r = 0; r < rounds; ++r) {
+    uint64_t e = r * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool mine = false;
+    uint64_t key = 0;
+    if (e < g.ne) {
+      uint32_t s, d;
+      gen_edge(g, seed_mixed, e, s, d);
+      if (d >= row_left && d - row_left < n_part) { mine = true; key = ((uint64_t)(d - row_left) << 32) | s; }
+    }
+    unsigned m = __ballot_sync(0xffffffffu, mine);  // warp-aggregated append
+    if (m) {
+      unsigned long long base = 0;
+      int leader = __ffs(m) - 1;
+      if ((int)lane == leader) base = atomicAdd(cursor, (unsigned long long)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (mine) {
+        uint64_t pos = base + __popc(m & ((1u << lane) - 1));
+        if (pos < capacity) keys[pos] = key;
+      }
+    }
+  }
+}
+
+__global__ void keys_to_src_kernel(const uint64_t* __restrict__ keys, uint64_t n, uint32_t* __restrict__ src,
+                                   int32_t* __restrict__ weight, uint64_t seed, uint32_t row_left) {
+  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t k = keys[e];
+    uint32_t s = (uint32_t)k;
+    src[e] = s;
+    if (weight) {
+      uint32_t d = (uint32_t)(k >> 32) + row_left;
+      uint32_t lo = s < d ? s : d, hi = s < d ? d : s;
+      weight[e] = edge_weight(seed, lo, hi);
+    }
+  }
+}
+
+// The reference's greedy edge-balanced split (pull_model.inl:108-131): walking v upward, close a partition AT v
+// (inclusive) as soon as the edges accumulated since `left` exceed cap = ceil(ne/P).  Since the running count is
+// row_end[v] - base, each cut is the smallest v with row_end[v] - base > cap: a binary search.  Trailing remainder
+// becomes the last partition; if fewer than P result, the rest are empty (row_left = nv, n = 0).
+__global__ void partition_kernel(const uint64_t* __restrict__ row_end, uint32_t nv, uint64_t ne, int P,
+                                 uint32_t* row_left, uint32_t* n_part, uint64_t* col_left, int* count_out) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  uint64_t cap = (ne + P - 1) / P;
+  uint32_t left = 0;
+  int count = 0, found_adjust = 0;
+  while (left < nv && count < P) {
+    uint64_t base = left == 0 ? 0 : row_end[left - 1];
+    uint32_t lo = left, hi = nv;  // first v in [left, nv) with row_end[v] - base > cap, or nv
+    while (lo < hi) {
+      uint32_t mid = lo + (hi - lo) / 2;
+      if (row_end[mid] - base > cap) hi = mid; else lo = mid + 1;
+    }
+    if (lo < nv) {
+      row_left[count] = left; n_part[count] = lo - left + 1; col_left[count] = base; ++count;
+      left = lo + 1;
+    } else {
+      // remainder: always kept (see host_partition in api.cu); only counted as "found" when it holds edges
+      if (row_end[nv - 1] - base == 0) --found_adjust;
+      row_left[count] = left; n_part[count] = nv - left; col_left[count] = base; ++count;
+      left = nv;
+    }
+  }
+  *count_out = count + found_adjust;
+  for (int p = count; p < P; ++p) { row_left[p] = nv; n_part[p] = 0; col_left[p] = ne; }
+}
+
+__global__ void widen_u32_to_u64_kernel(const uint32_t* __restrict__ in, uint64_t* __restrict__ out, uint64_t n) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = in[i];
+}
+
+// local layout: rel[i] = row_end_global[row_left + i] - col_left for i < n_part, then 4 sentinels (~0)
+__global__ void rowend_rel_kernel(const uint64_t* __restrict__ row_end_global, uint32_t row_left, uint32_t n_part,
+                                  uint64_t col_left, uint64_t* __restrict__ rel) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (uint64_t)n_part + 4;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    rel[i] = i < n_part ? row_end_global[row_left + i] - col_left : ~0ull;
+}
+
+__global__ void hist_src_kernel(const uint32_t* __restrict__ src, uint64_t n, uint32_t* __restrict__ cnt) {
+  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x)
+    atomicAdd(cnt + src[e], 1u);
+}
+
+// dst (global id) of every local edge: upper_bound over the relative row_end array
+__global__ void edge_dst_kernel(const uint64_t* __restrict__ row_end_rel, uint32_t n_part, uint64_t e_part,
+                                uint32_t row_left, uint32_t* __restrict__ dst) {
+  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < e_part; e += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t lo = 0, hi = n_part;  // first i with row_end_rel[i] > e
+    while (lo < hi) {
+      uint32_t mid = lo + (hi - lo) / 2;
+      if (row_end_rel[mid] > e) hi = mid; else lo = mid + 1;
+    }
+    dst[e] = row_left + lo;
+  }
+}
+
+template <class T>
+__global__ void fill_kernel(T* p, uint64_t n, T v) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+__global__ void iota_kernel(uint32_t* p, uint64_t n) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = (uint32_t)i;
+}
+
+// PageRank init: x0[v] = (1/nv)/deg[v], or 1/nv for deg 0  (pagerank_gpu.cu:255-259)
+__global__ void pr_init_kernel(const uint32_t* __restrict__ deg, uint32_t nv, float* __restrict__ x) {
+  float rank = __fdiv_rn(1.0f, (float)nv);
+  for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t d = deg[v];
+    x[v] = d == 0 ? rank : __fdiv_rn(rank, (float)d);
+  }
+}
+
+}  // namespace luxb

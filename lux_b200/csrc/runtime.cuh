@@ -1,0 +1,73 @@
+// runtime.cuh — the per-rank host runtime state (replaces Graph + GraphPiece, core/graph.h:54-98, and the
+// placement/ownership role of LuxMapper + Realm's FB allocator).  One luxb_graph = one rank = one GPU.
+#pragma once
+#include <vector>
+#include "comm.h"
+#include "common.cuh"
+
+struct luxb_graph {
+  luxb_config cfg{};
+  uint32_t nv = 0;
+  uint64_t ne = 0;
+  int P = 1;
+  int parts_found = 0;  // partitions the reference's greedy scan produced (== P when the reference would accept)
+  bool weighted = false;
+
+  // global partition table (Graph::rowLeft/rowRight, core/graph.h:62)
+  uint32_t rl[LUXB_MAX_PARTS]{};
+  uint32_t np[LUXB_MAX_PARTS]{};
+  uint64_t cl[LUXB_MAX_PARTS]{};
+  uint32_t cap[LUXB_MAX_PARTS]{};      // frontier queue capacity per partition (push_model.inl:393)
+  uint64_t slot_off[LUXB_MAX_PARTS]{}; // our slot offsets inside fq buffers
+  uint64_t slot_bytes[LUXB_MAX_PARTS]{};
+  uint64_t fq_total = 0;
+
+  // this rank's slice
+  uint32_t row_left = 0, n_part = 0;
+  uint64_t col_left = 0, e_part = 0;
+  uint64_t* d_row_end = nullptr;  // [n_part + 4] relative end offsets + sentinels
+  uint32_t* d_src = nullptr;      // [e_part + 8]
+  int32_t* d_weight = nullptr;    // [e_part + 8] (col_filter)
+  uint32_t* d_tile_v = nullptr;
+  uint32_t n_tiles = 0;
+  void* d_head = nullptr;
+  void* d_tail = nullptr;
+
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  int num_sms = 0;
+
+  // app state
+  bool inited = false;
+  uint32_t* d_deg = nullptr;   // PageRank: global out-degrees
+  void* d_val[2] = {nullptr, nullptr};  // replicas of the vertex values (labels: only [0])
+  int cur = 0;
+  size_t vbytes = 4;           // bytes per vertex value
+  // push apps
+  uint32_t* d_cur = nullptr;       // [n_part] working labels of this partition
+  uint64_t* d_out_end = nullptr;   // [nv] CSR-by-source end offsets over this partition's edges
+  uint32_t* d_out_dst = nullptr;   // [e_part]
+  unsigned char* d_fq_all = nullptr;  // every partition's frontier slot as exchanged
+  unsigned char* d_fq_new = nullptr;  // this partition's slot under construction
+  unsigned char* d_fq_tmp = nullptr;
+  uint32_t* d_hdr_all = nullptr;      // [2 * P] gathered headers
+  uint32_t* h_hdr = nullptr;          // pinned [2 * P]: type, count of the current frontier of every partition
+  uint32_t* h_scratch = nullptr;      // pinned scratch (header readback)
+  unsigned long long* d_counters = nullptr;  // [0] edges scanned by push kernels, [1] check mistakes
+  // col_filter
+  uint32_t* d_chunk_first = nullptr;
+  uint32_t* d_chunk_vtx = nullptr;
+  uint32_t n_chunks = 0;
+  float* d_partial = nullptr;
+
+  // communication
+  luxb::ncclComm_t comm = nullptr;
+  bool p2p_ready = false;
+  void* peer_val[2][LUXB_MAX_PARTS]{};  // imported replicas of the peers (P2P exchange)
+  uint32_t* d_sync = nullptr;
+
+  // stats / trace
+  luxb_stats_t stats{};
+  std::vector<uint64_t> trace_active;
+  std::vector<int32_t> trace_pull;
+};
