@@ -144,10 +144,22 @@ typedef struct {
   uint64_t kernel_launches;  /* our kernels launched by iterate calls */
   uint64_t last_active;      /* global active count after the last iteration */
   uint32_t last_frontier_type; /* this rank's frontier representation after the last iteration */
+  double dominant_kernel_seconds;   /* with kernel timing on: device time inside the gather kernel(s) only */
+  uint64_t dominant_kernel_launches;
 } luxb_stats_t;
 int luxb_stats(const luxb_graph* g, luxb_stats_t* out);
 /* Per-iteration trace of push apps (global active count, direction) for parity tests; returns #entries copied. */
 int luxb_trace(const luxb_graph* g, uint64_t* active, int32_t* pull, int max_entries);
+
+/* Bracket every launch of the dominant (edge gather) kernel with CUDA events on the launching stream so that the
+ * bench can report its average duration for the roofline (stats.dominant_kernel_*).  Off by default. */
+int luxb_enable_kernel_timing(luxb_graph* g, int on);
+/* PageRank: the global out-degree array computed by the scan phase (pull_scan_task_impl, pull_model.inl:322-345). */
+int luxb_get_out_degree(luxb_graph* g, luxb_vid* host_out, size_t bytes);
+
+/* Dev tooling: time a bare gather sweep (no reduction) over this partition's source ids, natural (packed = 0) or
+ * hot-packed (packed = 1) layout — the memory-system ceiling the pull kernel is compared against. */
+int luxb_debug_gather_ms(luxb_graph* g, int packed, float* ms_out);
 
 /* Raw device pointers for tooling (bench roofline timing, torch interop); not needed by normal callers. */
 typedef struct {

@@ -34,7 +34,8 @@ class _Config(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("loop_seconds", C.c_double), ("iterations", C.c_uint64), ("edges_processed", C.c_uint64),
                 ("pull_iterations", C.c_uint64), ("kernel_launches", C.c_uint64), ("last_active", C.c_uint64),
-                ("last_frontier_type", C.c_uint32)]
+                ("last_frontier_type", C.c_uint32), ("dominant_kernel_seconds", C.c_double),
+                ("dominant_kernel_launches", C.c_uint64)]
 
 
 class DeviceView(C.Structure):
@@ -234,6 +235,20 @@ class LuxGraph:
         p = np.zeros(max_entries, np.int32)
         n = _chk(load_library().luxb_trace(self._h, _p(a), _p(p), C.c_int(max_entries)), "luxb_trace")
         return a[:n].copy(), p[:n].copy()
+
+    def enable_kernel_timing(self, on=True):
+        _chk(load_library().luxb_enable_kernel_timing(self._h, C.c_int(1 if on else 0)), "luxb_enable_kernel_timing")
+
+    def out_degree(self, out=None):
+        if out is None:
+            out = np.empty(self.nv, np.uint32)
+        _chk(load_library().luxb_get_out_degree(self._h, _p(out), C.c_size_t(out.nbytes)), "luxb_get_out_degree")
+        return out
+
+    def debug_gather_ms(self, packed=True):
+        ms = C.c_float(0)
+        _chk(load_library().luxb_debug_gather_ms(self._h, C.c_int(1 if packed else 0), C.byref(ms)), "luxb_debug_gather_ms")
+        return ms.value
 
     def device_view(self):
         v = DeviceView()

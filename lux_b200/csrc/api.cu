@@ -45,7 +45,18 @@ void set_error(const char* fmt, ...) {
     }                                                                                                \
   } while (0)
 
-using PullShapeDefault = PullShape<128, 17, 2>;
+// merge-path shapes <items per lane, consumer warps per CTA, ring stages>; chosen at open time (LUXB_PULL_SHAPE).
+// Shared memory is kept small on purpose: what the ring does not take stays L1, and the gather rate follows L1 size.
+#define LUXB_PULL_SHAPES(X) \
+  X(0, 7, 8, 2) X(1, 9, 8, 2) X(2, 11, 8, 2) X(3, 13, 8, 2) X(4, 15, 8, 2) X(5, 7, 16, 2) X(6, 9, 16, 2) X(7, 11, 16, 2) \
+  X(8, 11, 8, 3) X(9, 5, 16, 2)
+#define LUXB_DECL_SHAPE(id, ipt, warps, stages) using PullShape##id = PullShape<ipt, warps, stages>;
+LUXB_PULL_SHAPES(LUXB_DECL_SHAPE)
+#define LUXB_TILE_OF(id, ipt, warps, stages) PullShape##id::kTile,
+static const int kPullTileOf[] = {LUXB_PULL_SHAPES(LUXB_TILE_OF)};
+static const int kNumPullShapes = sizeof(kPullTileOf) / sizeof(int);
+static const int kDefaultPullShape = 0;
+static const int kDefaultPullCtas = 3;
 
 static inline int grid_for(uint64_t n, int threads, int cap) {
   uint64_t b = (n + threads - 1) / threads;
@@ -141,15 +152,30 @@ static void set_partition_derived(luxb_graph* g) {
 // after d_row_end / d_src are in place: merge-path tile table + per-tile partial buffers
 static int finish_layout(luxb_graph* g) {
   uint64_t total = (uint64_t)g->n_part + g->e_part;
-  uint64_t nt = (total + PullShapeDefault::kTile - 1) / PullShapeDefault::kTile;
+  g->pull_shape = kDefaultPullShape;
+  if (const char* env = getenv("LUXB_PULL_SHAPE")) {
+    int v = atoi(env);
+    if (v >= 0 && v < kNumPullShapes) g->pull_shape = v;
+  }
+  const uint32_t tile = (uint32_t)kPullTileOf[g->pull_shape];
+  uint64_t nt = (total + tile - 1) / tile;
   LUXB_ARG(nt < 0xFFFFFFFFull, "partition too large for the tile table");
   g->n_tiles = (uint32_t)nt;
   LUXB_TRY(dmalloc(&g->d_tile_v, (uint64_t)g->n_tiles + 2));
   tile_table_kernel<<<grid_for((uint64_t)g->n_tiles + 1, 256, 1 << 20), 256, 0, g->stream>>>(
-      g->d_row_end, g->n_part, g->e_part, PullShapeDefault::kTile, g->n_tiles, g->d_tile_v);
+      g->d_row_end, g->n_part, g->e_part, tile, g->n_tiles, g->d_tile_v);
+  LUXB_CUDA(cudaGetLastError());
+  LUXB_TRY(dmalloc(&g->d_row_end32, (uint64_t)g->n_part + 8));
+  narrow_u64_to_u32_kernel<<<grid_for((uint64_t)g->n_part + 8, 256, 4096), 256, 0, g->stream>>>(g->d_row_end, g->n_part + 4,
+                                                                                          g->d_row_end32, (uint64_t)g->n_part + 8);
   LUXB_CUDA(cudaGetLastError());
   LUXB_TRY(dmalloc((uint32_t**)&g->d_head, (uint64_t)g->n_tiles + 1));
   LUXB_TRY(dmalloc((uint32_t**)&g->d_tail, (uint64_t)g->n_tiles + 1));
+  g->n_fix_blocks = (g->n_tiles + kFixBlock - 1) / kFixBlock;
+  LUXB_TRY(dmalloc((uint64_t**)&g->d_carry, (uint64_t)g->n_tiles + 1));
+  LUXB_TRY(dmalloc(&g->d_carry_flag, (uint64_t)g->n_tiles + 1));
+  LUXB_TRY(dmalloc((uint64_t**)&g->d_block_agg, (uint64_t)g->n_fix_blocks + 1));
+  LUXB_TRY(dmalloc(&g->d_block_flag, (uint64_t)g->n_fix_blocks + 1));
   LUXB_TRY(dmalloc(&g->d_counters, 4));
   LUXB_CUDA(cudaMemsetAsync(g->d_counters, 0, 4 * sizeof(unsigned long long), g->stream));
   LUXB_CUDA(cudaStreamSynchronize(g->stream));
@@ -561,6 +587,78 @@ static int reset_label_state(luxb_graph* g, bool all_active) {
   return 0;
 }
 
+// Choose the hot set (largest out-degrees, at most LUXB_HOT_MB megabytes of values, default 64 MB ~ half of L2) and
+// rewrite this partition's source ids as indices into Z = [hot copy | natural] (see build.cuh).
+static int build_hot_layout(luxb_graph* g) {
+  g->hot_n = 0;
+  double hot_mb = 64.0;
+  if (const char* env = getenv("LUXB_HOT_MB")) hot_mb = atof(env);
+  uint64_t h_max = (uint64_t)(hot_mb * 1e6 / 4.0);
+  if (h_max == 0 || g->nv < 2 || (uint64_t)g->nv >= 0xFFFFFFFFull - h_max) return 0;
+  if (h_max > g->nv) h_max = g->nv;
+  const int grid = g->num_sms * 8;
+  const uint32_t cap = 4096;
+  unsigned long long* d_hist = nullptr;
+  LUXB_TRY(dmalloc(&d_hist, cap + 1));
+  LUXB_CUDA(cudaMemsetAsync(d_hist, 0, (cap + 1) * 8, g->stream));
+  degree_hist_kernel<<<grid, 256, 0, g->stream>>>(g->d_deg, g->nv, cap, d_hist);
+  std::vector<unsigned long long> hist(cap + 1);
+  LUXB_CUDA(cudaMemcpyAsync(hist.data(), d_hist, (cap + 1) * 8, cudaMemcpyDeviceToHost, g->stream));
+  LUXB_CUDA(cudaStreamSynchronize(g->stream));
+  LUXB_CUDA(cudaFree(d_hist));
+  // smallest tau >= 2 with |{deg >= tau}| <= h_max  (degree-1 vertices are gathered once: packing cannot help them)
+  uint64_t above = 0;
+  uint32_t tau = cap + 1;
+  for (uint32_t d = cap; d >= 2; --d) {
+    if (above + hist[d] > h_max) break;
+    above += hist[d];
+    tau = d;
+  }
+  if (above == 0 || tau > cap) return 0;
+  const uint32_t H = (uint32_t)above;
+  uint32_t *d_keys = nullptr, *d_ids = nullptr, *d_keys2 = nullptr, *d_map = nullptr;
+  unsigned int* d_cursor = nullptr;
+  LUXB_TRY(dmalloc(&d_keys, H));
+  LUXB_TRY(dmalloc(&d_keys2, H));
+  LUXB_TRY(dmalloc(&d_ids, H));
+  LUXB_TRY(dmalloc(&g->d_hot_order, H));
+  LUXB_TRY(dmalloc(&d_cursor, 1));
+  LUXB_CUDA(cudaMemsetAsync(d_cursor, 0, 4, g->stream));
+  hot_select_kernel<<<grid, 256, 0, g->stream>>>(g->d_deg, g->nv, tau, d_cursor, d_keys, d_ids, H);
+  LUXB_CUDA(cudaGetLastError());
+  // ids are appended in nondeterministic order: sort by (key, id) = two stable passes (id first, then key)
+  size_t tb = 0;
+  void* d_tmp = nullptr;
+  int vbits = 1;
+  while ((1ull << vbits) < (uint64_t)g->nv) ++vbits;
+  LUXB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, d_ids, g->d_hot_order, d_keys, d_keys2, (int)H, 0, vbits, g->stream));
+  LUXB_CUDA(cudaMalloc(&d_tmp, tb + 256));
+  LUXB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb, d_ids, g->d_hot_order, d_keys, d_keys2, (int)H, 0, vbits, g->stream));
+  LUXB_CUDA(cudaStreamSynchronize(g->stream));
+  LUXB_CUDA(cudaFree(d_tmp));
+  tb = 0;
+  LUXB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, d_keys2, d_keys, g->d_hot_order, d_ids, (int)H, 0, 32, g->stream));
+  LUXB_CUDA(cudaMalloc(&d_tmp, tb + 256));
+  LUXB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb, d_keys2, d_keys, g->d_hot_order, d_ids, (int)H, 0, 32, g->stream));
+  LUXB_CUDA(cudaMemcpyAsync(g->d_hot_order, d_ids, (size_t)H * 4, cudaMemcpyDeviceToDevice, g->stream));
+  LUXB_TRY(dmalloc(&d_map, g->nv));
+  gather_map_init_kernel<<<grid, 256, 0, g->stream>>>(d_map, g->nv, H);
+  gather_map_hot_kernel<<<grid, 256, 0, g->stream>>>(d_map, g->d_hot_order, H);
+  LUXB_TRY(dmalloc(&g->d_src_gather, g->e_part + 8));
+  LUXB_CUDA(cudaMemsetAsync(g->d_src_gather, 0, (g->e_part + 8) * 4, g->stream));
+  remap_src_kernel<<<grid, 256, 0, g->stream>>>(g->d_src, g->e_part, d_map, g->d_src_gather);
+  LUXB_CUDA(cudaGetLastError());
+  LUXB_CUDA(cudaStreamSynchronize(g->stream));
+  LUXB_CUDA(cudaFree(d_tmp));
+  LUXB_CUDA(cudaFree(d_keys));
+  LUXB_CUDA(cudaFree(d_keys2));
+  LUXB_CUDA(cudaFree(d_ids));
+  LUXB_CUDA(cudaFree(d_cursor));
+  LUXB_CUDA(cudaFree(d_map));
+  g->hot_n = H;
+  return 0;
+}
+
 int luxb_init(luxb_graph* g) {
   LUXB_ARG(g != nullptr, "graph is NULL");
   if (g->inited) { set_error("luxb_init called twice"); return LUXB_ERR_STATE; }
@@ -575,9 +673,12 @@ int luxb_init(luxb_graph* g) {
       hist_src_kernel<<<grid, 256, 0, g->stream>>>(g->d_src, g->e_part, g->d_deg);  // pull_scan_task_impl
       LUXB_CUDA(cudaGetLastError());
       if (g->P > 1) LUXB_NCCL(nccl().AllReduce(g->d_deg, g->d_deg, g->nv, ncclUint32, ncclSum, g->comm, g->stream));
-      for (int k = 0; k < 2; ++k) LUXB_TRY(dmalloc((float**)&g->d_val[k], g->nv));
-      pr_init_kernel<<<grid, 256, 0, g->stream>>>(g->d_deg, g->nv, (float*)g->d_val[0]);
-      LUXB_CUDA(cudaMemsetAsync(g->d_val[1], 0, (size_t)g->nv * 4, g->stream));
+      LUXB_TRY(build_hot_layout(g));
+      for (int k = 0; k < 2; ++k) LUXB_TRY(dmalloc((float**)&g->d_val[k], (uint64_t)g->hot_n + g->nv));
+      pr_init_kernel<<<grid, 256, 0, g->stream>>>(g->d_deg, g->nv, (float*)g->d_val[0] + g->hot_n);
+      LUXB_CUDA(cudaMemsetAsync(g->d_val[1], 0, ((size_t)g->hot_n + g->nv) * 4, g->stream));
+      if (g->hot_n)
+        hot_refresh_kernel<float><<<grid_for(g->hot_n, 256, grid), 256, 0, g->stream>>>((float*)g->d_val[0], g->d_hot_order, g->hot_n);
       LUXB_CUDA(cudaGetLastError());
       break;
     }
@@ -654,64 +755,112 @@ static int p2p_barrier(luxb_graph* g) {
 }
 
 extern "C++" {
+template <class Prog, class Shape>
+static int launch_pull_shape(luxb_graph* g, const PullArgs<Prog>& a) {
+  static int attr_ctas = -1;
+  static int occ = 0;
+  auto kern = pull_tile_kernel<Prog, Shape>;
+  int want = kDefaultPullCtas;
+  if (const char* env = getenv("LUXB_PULL_CTAS")) want = atoi(env);
+  if (want < 1) want = 1;
+  if (attr_ctas != want) {
+    // carve out exactly `want` CTAs' worth of shared memory; the rest of the 256 KB unified array stays L1
+    LUXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Shape::kSmemBytes));
+    int carve_pct = (int)std::min<size_t>(100, (want * (Shape::kSmemBytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+    LUXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve_pct));
+    LUXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Shape::kThreads, Shape::kSmemBytes));
+    if (occ < 1) occ = 1;
+    if (occ > want) occ = want;
+    attr_ctas = want;
+  }
+  const uint32_t n_super = (g->n_tiles + Shape::kWarps - 1) / Shape::kWarps;
+  uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)g->num_sms * occ, n_super);
+  kern<<<grid, Shape::kThreads, Shape::kSmemBytes, g->stream>>>(a);
+  LUXB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <class Prog>
-static int launch_pull(luxb_graph* g, const typename Prog::Vertex* x_old, typename Prog::Vertex* out_local,
-                       const typename Prog::Params& prm, int out_replica /* -1: no peers */) {
-  using Shape = PullShapeDefault;
+static int launch_pull(luxb_graph* g, const typename Prog::Vertex* x_gather, const typename Prog::Vertex* x_nat,
+                       const uint32_t* src_idx, typename Prog::Vertex* out_local, const typename Prog::Params& prm,
+                       int out_replica /* -1: no peers */) {
   if (g->n_tiles == 0) return 0;
   PullArgs<Prog> a{};
   a.row_end = g->d_row_end;
-  a.src = g->d_src;
+  a.row_end32 = g->d_row_end32;
+  a.src = src_idx;
+  a.x_nat = x_nat;
   a.tile_v = g->d_tile_v;
   a.n_part = g->n_part;
   a.e_part = g->e_part;
   a.n_tiles = g->n_tiles;
   a.row_left = g->row_left;
-  a.x_old = x_old;
+  a.x_old = x_gather;
   a.out = out_local;
   a.head_partial = reinterpret_cast<typename Prog::Acc*>(g->d_head);
   a.tail_partial = reinterpret_cast<typename Prog::Acc*>(g->d_tail);
+  a.carry = reinterpret_cast<typename Prog::Wide*>(g->d_carry);
+  a.carry_flag = g->d_carry_flag;
+  a.block_agg = reinterpret_cast<typename Prog::Wide*>(g->d_block_agg);
+  a.block_flag = g->d_block_flag;
+  a.tile_counter = reinterpret_cast<uint32_t*>(g->d_counters + 2);
+  LUXB_CUDA(cudaMemsetAsync(a.tile_counter, 0, 4, g->stream));
   a.prm = prm;
   a.n_peers = 0;
   if (out_replica >= 0 && g->p2p_ready && g->cfg.exchange == LUXB_EXCHANGE_P2P) {
     for (int p = 0; p < g->P; ++p) {
       if (p == g->cfg.rank) continue;
-      a.peer_out[a.n_peers++] = reinterpret_cast<typename Prog::Vertex*>(g->peer_val[out_replica][p]) + g->row_left;
+      a.peer_out[a.n_peers++] = reinterpret_cast<typename Prog::Vertex*>(g->peer_val[out_replica][p]) + g->hot_n + g->row_left;
     }
   }
-  static bool attr_set = false;
-  auto kern = pull_tile_kernel<Prog, Shape>;
-  if (!attr_set) {
-    LUXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Shape::kSmemBytes));
-    attr_set = true;
+  if (g->kernel_timing) {
+    if (g->kt_used + 2 > g->kt_events.size()) {
+      cudaEvent_t e0, e1;
+      LUXB_CUDA(cudaEventCreate(&e0));
+      LUXB_CUDA(cudaEventCreate(&e1));
+      g->kt_events.push_back(e0);
+      g->kt_events.push_back(e1);
+    }
+    LUXB_CUDA(cudaEventRecord(g->kt_events[g->kt_used], g->stream));
   }
-  int occ = 0;
-  LUXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Shape::kThreads, Shape::kSmemBytes));
-  if (occ < 1) occ = 1;
-  uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)g->num_sms * occ, g->n_tiles);
-  kern<<<grid, Shape::kThreads, Shape::kSmemBytes, g->stream>>>(a);
-  LUXB_CUDA(cudaGetLastError());
+  switch (g->pull_shape) {
+#define LUXB_CASE_SHAPE(id, ipt, warps, stages) \
+    case id: LUXB_TRY((launch_pull_shape<Prog, PullShape##id>(g, a))); break;
+    LUXB_PULL_SHAPES(LUXB_CASE_SHAPE)
+    default: set_error("bad pull shape"); return LUXB_ERR_STATE;
+  }
+  if (g->kernel_timing) {
+    LUXB_CUDA(cudaEventRecord(g->kt_events[g->kt_used + 1], g->stream));
+    g->kt_used += 2;
+  }
   g->stats.kernel_launches++;
   if (g->n_tiles > 1) {
-    pull_fixup_kernel<Prog><<<(g->n_tiles - 1 + 255) / 256, 256, 0, g->stream>>>(a);
+    pull_fixup_scan_kernel<Prog><<<g->n_fix_blocks, kFixBlock, 0, g->stream>>>(a);
+    pull_fixup_blocks_kernel<Prog><<<1, 1024, 0, g->stream>>>(a, g->n_fix_blocks);
+    pull_fixup_apply_kernel<Prog><<<g->n_fix_blocks, kFixBlock, 0, g->stream>>>(a);
     LUXB_CUDA(cudaGetLastError());
-    g->stats.kernel_launches++;
+    g->stats.kernel_launches += 3;
   }
   return 0;
 }
-
 }  // extern "C++"
 
 static int pagerank_iteration(luxb_graph* g) {
   PageRankProgram::Params prm;
   prm.init_rank = (1.0f - kAlpha) / (float)g->nv;  // pagerank_gpu.cu:144
   prm.deg = g->d_deg;
-  float* x_old = (float*)g->d_val[g->cur];
-  float* x_new = (float*)g->d_val[1 - g->cur];
-  LUXB_TRY(launch_pull<PageRankProgram>(g, x_old, x_new + g->row_left, prm, 1 - g->cur));
+  float* z_old = (float*)g->d_val[g->cur];  // [hot copy | natural]
+  float* z_new = (float*)g->d_val[1 - g->cur];
+  LUXB_TRY(launch_pull<PageRankProgram>(g, z_old, z_old + g->hot_n, g->hot_n ? g->d_src_gather : g->d_src,
+                                        z_new + g->hot_n + g->row_left, prm, 1 - g->cur));
   if (g->P > 1) {
     if (g->p2p_ready && g->cfg.exchange == LUXB_EXCHANGE_P2P) LUXB_TRY(p2p_barrier(g));
-    else LUXB_TRY(allgather_slices(g, x_new, 4));
+    else LUXB_TRY(allgather_slices(g, z_new + g->hot_n, 4));
+  }
+  if (g->hot_n) {  // every rank refreshes its hot copies from the (now complete) natural part
+    hot_refresh_kernel<float><<<grid_for(g->hot_n, 256, g->num_sms * 8), 256, 0, g->stream>>>(z_new, g->d_hot_order, g->hot_n);
+    LUXB_CUDA(cudaGetLastError());
+    g->stats.kernel_launches++;
   }
   g->cur ^= 1;
   g->stats.edges_processed += g->e_part;
@@ -776,7 +925,7 @@ static int label_iteration(luxb_graph* g) {
 
   if (pull) {
     typename Prog::Params prm{0};
-    LUXB_TRY(launch_pull<Prog>(g, lab, g->d_cur, prm, -1));
+    LUXB_TRY(launch_pull<Prog>(g, lab, lab, g->d_src, g->d_cur, prm, -1));
     g->stats.edges_processed += g->e_part;
     g->stats.pull_iterations++;
   } else if (g->n_part && old_size) {
@@ -925,6 +1074,13 @@ static int finish_timed(luxb_graph* g) {
   float ms = 0.f;
   LUXB_CUDA(cudaEventElapsedTime(&ms, g->ev_begin, g->ev_end));
   g->stats.loop_seconds += ms * 1e-3;
+  for (size_t k = 0; k + 1 < g->kt_used; k += 2) {
+    float kms = 0.f;
+    LUXB_CUDA(cudaEventElapsedTime(&kms, g->kt_events[k], g->kt_events[k + 1]));
+    g->stats.dominant_kernel_seconds += kms * 1e-3;
+    g->stats.dominant_kernel_launches++;
+  }
+  g->kt_used = 0;
   if (g->d_out_end) {
     unsigned long long scanned = 0;
     LUXB_CUDA(cudaMemcpy(&scanned, g->d_counters, 8, cudaMemcpyDeviceToHost));
@@ -973,7 +1129,8 @@ int luxb_get_values(luxb_graph* g, void* host_out, size_t bytes) {
   size_t need = (size_t)g->nv * g->vbytes;
   LUXB_ARG(bytes == need, "buffer is %zu bytes, vertex values need %zu", bytes, need);
   LUXB_CUDA(cudaSetDevice(g->cfg.device));
-  const void* srcp = (g->cfg.app == LUXB_CC || g->cfg.app == LUXB_SSSP) ? g->d_val[0] : g->d_val[g->cur];
+  const char* srcp = (const char*)((g->cfg.app == LUXB_CC || g->cfg.app == LUXB_SSSP) ? g->d_val[0] : g->d_val[g->cur]);
+  srcp += (size_t)g->hot_n * g->vbytes;  // natural-order part of Z
   LUXB_CUDA(cudaMemcpyAsync(host_out, srcp, need, cudaMemcpyDeviceToHost, g->stream));
   LUXB_CUDA(cudaStreamSynchronize(g->stream));
   return 0;
@@ -986,8 +1143,10 @@ int luxb_set_values(luxb_graph* g, const void* host_in, size_t bytes) {
   LUXB_ARG(bytes == need, "buffer is %zu bytes, vertex values need %zu", bytes, need);
   LUXB_CUDA(cudaSetDevice(g->cfg.device));
   const bool labels = g->cfg.app == LUXB_CC || g->cfg.app == LUXB_SSSP;
-  void* dstp = labels ? g->d_val[0] : g->d_val[g->cur];
-  LUXB_CUDA(cudaMemcpyAsync(dstp, host_in, need, cudaMemcpyHostToDevice, g->stream));
+  char* dstp = (char*)(labels ? g->d_val[0] : g->d_val[g->cur]);
+  LUXB_CUDA(cudaMemcpyAsync(dstp + (size_t)g->hot_n * g->vbytes, host_in, need, cudaMemcpyHostToDevice, g->stream));
+  if (g->hot_n)
+    hot_refresh_kernel<float><<<grid_for(g->hot_n, 256, g->num_sms * 8), 256, 0, g->stream>>>((float*)dstp, g->d_hot_order, g->hot_n);
   if (labels) LUXB_TRY(reset_label_state(g, true));
   LUXB_CUDA(cudaStreamSynchronize(g->stream));
   return 0;
@@ -1032,10 +1191,62 @@ int luxb_trace(const luxb_graph* g, uint64_t* active, int32_t* pull, int max_ent
   return n;
 }
 
+int luxb_enable_kernel_timing(luxb_graph* g, int on) {
+  LUXB_ARG(g != nullptr, "graph is NULL");
+  g->kernel_timing = on != 0;
+  return 0;
+}
+
+int luxb_get_out_degree(luxb_graph* g, luxb_vid* host_out, size_t bytes) {
+  LUXB_ARG(g && host_out, "NULL argument");
+  if (!g->inited || !g->d_deg) { set_error("out-degrees exist only for an initialised PageRank graph"); return LUXB_ERR_STATE; }
+  LUXB_ARG(bytes == (size_t)g->nv * 4, "buffer must hold nv u32");
+  LUXB_CUDA(cudaSetDevice(g->cfg.device));
+  LUXB_CUDA(cudaMemcpyAsync(host_out, g->d_deg, bytes, cudaMemcpyDeviceToHost, g->stream));
+  LUXB_CUDA(cudaStreamSynchronize(g->stream));
+  return 0;
+}
+
+// dev tooling: raw gather rate over this partition's (possibly hot-packed) source ids, no reduction structure
+__global__ void debug_gather_kernel(const uint32_t* __restrict__ idx, const float* __restrict__ x, uint64_t m, float* out) {
+  float acc = 0.f;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; base < m; base += stride * 8) {
+    uint32_t id[8];
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { uint64_t i = base + k * stride; id[k] = i < m ? __ldg(idx + i) : 0; }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __ldg(x + id[k]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += v[k];
+  }
+  if (acc == 123.456f) out[0] = acc;
+}
+
+int luxb_debug_gather_ms(luxb_graph* g, int packed, float* ms_out) {
+  LUXB_ARG(g && ms_out && g->inited && g->cfg.app == LUXB_PAGERANK, "needs an initialised PageRank graph");
+  LUXB_CUDA(cudaSetDevice(g->cfg.device));
+  const uint32_t* idx = (packed && g->hot_n) ? g->d_src_gather : g->d_src;
+  const float* x = (const float*)g->d_val[g->cur] + ((packed && g->hot_n) ? 0 : g->hot_n);
+  float best = 1e30f;
+  for (int r = 0; r < 4; ++r) {
+    LUXB_CUDA(cudaEventRecord(g->ev_begin, g->stream));
+    debug_gather_kernel<<<g->num_sms * 4, 256, 0, g->stream>>>(idx, x, g->e_part, (float*)g->d_head);
+    LUXB_CUDA(cudaEventRecord(g->ev_end, g->stream));
+    LUXB_CUDA(cudaStreamSynchronize(g->stream));
+    float ms = 0.f;
+    LUXB_CUDA(cudaEventElapsedTime(&ms, g->ev_begin, g->ev_end));
+    if (r > 0 && ms < best) best = ms;
+  }
+  *ms_out = best;
+  return 0;
+}
+
 int luxb_device_view_get(luxb_graph* g, luxb_device_view* out) {
   LUXB_ARG(g && out, "NULL argument");
   const bool labels = g->cfg.app == LUXB_CC || g->cfg.app == LUXB_SSSP;
-  out->values = g->inited ? (labels ? g->d_val[0] : g->d_val[g->cur]) : nullptr;
+  out->values = g->inited ? (void*)((char*)(labels ? g->d_val[0] : g->d_val[g->cur]) + (size_t)g->hot_n * g->vbytes) : nullptr;
   out->row_end = g->d_row_end;
   out->src = g->d_src;
   out->stream = g->stream;
@@ -1070,13 +1281,15 @@ void luxb_close(luxb_graph* g) {
         for (int k = 0; k < 2; ++k)
           if (g->peer_val[k][p]) cudaIpcCloseMemHandle(g->peer_val[k][p]);
   if (g->comm) nccl().CommDestroy(g->comm);
-  void* ptrs[] = {g->d_row_end, g->d_src, g->d_weight, g->d_tile_v, g->d_head, g->d_tail, g->d_deg, g->d_val[0], g->d_val[1],
+  void* ptrs[] = {g->d_row_end, g->d_row_end32, g->d_src, g->d_weight, g->d_tile_v, g->d_head, g->d_tail, g->d_deg, g->d_val[0], g->d_val[1],
                   g->d_cur, g->d_out_end, g->d_out_dst, g->d_fq_all, g->d_fq_new, g->d_fq_tmp, g->d_hdr_all, g->d_counters,
-                  g->d_chunk_first, g->d_chunk_vtx, g->d_partial, g->d_sync};
+                  g->d_chunk_first, g->d_chunk_vtx, g->d_partial, g->d_sync, g->d_hot_order, g->d_src_gather,
+                  g->d_carry, g->d_carry_flag, g->d_block_agg, g->d_block_flag};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (g->h_hdr) cudaFreeHost(g->h_hdr);
   if (g->h_scratch) cudaFreeHost(g->h_scratch);
+  for (cudaEvent_t e : g->kt_events) cudaEventDestroy(e);
   if (g->ev_begin) cudaEventDestroy(g->ev_begin);
   if (g->ev_end) cudaEventDestroy(g->ev_end);
   if (g->stream) cudaStreamDestroy(g->stream);

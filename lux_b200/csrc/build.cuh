@@ -158,6 +158,11 @@ __global__ void widen_u32_to_u64_kernel(const uint32_t* __restrict__ in, uint64_
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = in[i];
 }
 
+__global__ void narrow_u64_to_u32_kernel(const uint64_t* __restrict__ in, uint64_t n_in, uint32_t* __restrict__ out, uint64_t n_out) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += (uint64_t)gridDim.x * blockDim.x)
+    out[i] = i < n_in ? (uint32_t)in[i] : 0xFFFFFFFFu;
+}
+
 // local layout: rel[i] = row_end_global[row_left + i] - col_left for i < n_part, then 4 sentinels (~0)
 __global__ void rowend_rel_kernel(const uint64_t* __restrict__ row_end_global, uint32_t row_left, uint32_t n_part,
                                   uint64_t col_left, uint64_t* __restrict__ rel) {
@@ -191,6 +196,54 @@ __global__ void fill_kernel(T* p, uint64_t n, T v) {
 
 __global__ void iota_kernel(uint32_t* p, uint64_t n) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = (uint32_t)i;
+}
+
+// ---- hot-packed gather array (PageRank) -------------------------------------------------------------------------
+// Random 4-byte gathers are bounded by DRAM random-access rate (~48 G sectors/s measured on B200) unless they hit
+// L2 (~270 G/s).  Vertices are gathered in proportion to their out-degree, so the H vertices with the largest
+// out-degree are given a second, CONTIGUOUS home at the front of the value array Z = [hot copy (H) | natural (nv)]
+// and every source id is rewritten to point there: src' = rank(v) if hot else H + v.  Hot sectors then hold 8 hot
+// values instead of 1, the hot working set fits L2 (and the TLB reach), and cold gathers keep their natural order.
+__global__ void degree_hist_kernel(const uint32_t* __restrict__ deg, uint32_t nv, uint32_t cap, unsigned long long* __restrict__ hist) {
+  for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t d = deg[v];
+    atomicAdd(hist + (d < cap ? d : cap), 1ull);
+  }
+}
+
+// keys/vals for the hot vertices only (compacted with a warp-aggregated cursor); key ascending = degree descending
+__global__ void hot_select_kernel(const uint32_t* __restrict__ deg, uint32_t nv, uint32_t tau, unsigned int* cursor,
+                                  uint32_t* __restrict__ keys, uint32_t* __restrict__ ids, uint32_t capacity) {
+  const unsigned lane = threadIdx.x & 31;
+  uint64_t n_round = ((uint64_t)nv + 31) & ~31ull;
+  for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_round; v += (uint64_t)gridDim.x * blockDim.x) {
+    bool hot = v < nv && deg[v] >= tau;
+    unsigned m = __ballot_sync(0xffffffffu, hot);
+    if (m) {
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(cursor, (unsigned)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (hot) {
+        unsigned pos = base + __popc(m & ((1u << lane) - 1));
+        if (pos < capacity) { keys[pos] = 0xFFFFFFFFu - deg[v]; ids[pos] = (uint32_t)v; }
+      }
+    }
+  }
+}
+
+__global__ void gather_map_init_kernel(uint32_t* __restrict__ map, uint32_t nv, uint32_t H) {
+  for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (uint64_t)gridDim.x * blockDim.x) map[v] = H + (uint32_t)v;
+}
+__global__ void gather_map_hot_kernel(uint32_t* __restrict__ map, const uint32_t* __restrict__ order, uint32_t H) {
+  for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < H; h += (uint64_t)gridDim.x * blockDim.x) map[order[h]] = (uint32_t)h;
+}
+__global__ void remap_src_kernel(const uint32_t* __restrict__ src, uint64_t n, const uint32_t* __restrict__ map, uint32_t* __restrict__ out) {
+  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) out[e] = map[src[e]];
+}
+// refresh the hot copies from the natural part: Z[h] = Z[H + order[h]]
+template <class T>
+__global__ void hot_refresh_kernel(T* __restrict__ z, const uint32_t* __restrict__ order, uint32_t H) {
+  for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < H; h += (uint64_t)gridDim.x * blockDim.x) z[h] = z[(uint64_t)H + order[h]];
 }
 
 // PageRank init: x0[v] = (1/nv)/deg[v], or 1/nv for deg 0  (pagerank_gpu.cu:255-259)

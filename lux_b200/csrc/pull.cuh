@@ -1,55 +1,71 @@
 // pull.cuh — pull-model gather over a partition's CSC slice (replaces pr_kernel pagerank_gpu.cu:49-102 and
 // cc_pull_kernel / sssp_pull_kernel components_gpu.cu:85-130, sssp_gpu.cu:85-130).
 //
-// Design (B200-first, not a translation): the partition's work list is the MERGE of its nPart vertex-end markers
-// (row_end) and its ePart in-edges; it is cut into equal tiles of kTile merge items (merge-path), so every CTA
-// gets the same amount of (vertex + edge) work no matter how skewed the in-degrees are.  Per tile:
-//   1. one elected thread issues two TMA bulk copies (cp.async.bulk -> UBLKCP) that bring the tile's row_end slice
-//      and source-id slice into shared memory behind an mbarrier, kStages tiles ahead, L2 evict-first (streamed);
-//   2. all threads gather x_old[src] (read-only path, kIPT independent loads in flight per thread) and overwrite
-//      the source ids in shared memory with the gathered contributions;
-//   3. every thread walks kIPT consecutive merge items serially (conflict-free smem stride since kIPT is odd),
-//      producing complete per-vertex reductions plus one leading and one trailing partial; a fixed-shape
-//      segmented scan (warp shuffles + one smem hop) stitches partials across threads -> deterministic sums;
-//   4. a coalesced pass applies the vertex program's update() and stores the new values — to this GPU's replica
-//      and, in P2P exchange mode, straight into every peer GPU's replica (fused compute + all-gather).
-// Vertices whose edge list crosses a tile boundary are finished by pull_fixup_kernel from per-tile head/tail
-// partials in ascending tile order (fp64 for PageRank), so results do not depend on the grid size.
+// Design (B200-first, not a translation).  The partition's work list is the MERGE of its nPart vertex-end markers
+// (row_end) and its ePart in-edges (merge-path): cut into equal WARP TILES of W = 32 * kIPT merge items, so every
+// warp gets the same amount of (vertex + edge) work no matter how skewed the in-degrees are.  Warps are completely
+// independent — there is no __syncthreads in the hot loop — so the gather phase of one warp overlaps the reduction
+// phase of the others and the load/store unit (the measured bottleneck: one 32-byte sector per cycle per SM for
+// divergent 4-byte gathers) never idles.  Per warp tile:
+//   1. a producer warp streams the row_end words and source ids of kWarps consecutive warp tiles (one "super-tile")
+//      into a shared-memory ring with two TMA bulk copies (cp.async.bulk -> UBLKCP) behind a full/empty mbarrier
+//      pair per stage — measured: ~1 small bulk copy per 400 cycles per SM, so copies must be >= 10 KB to stay off
+//      the critical path.  L2 evict-first: streamed data must not displace the value array.  Consumer warps only
+//      meet at these mbarriers and may drift kStages-1 super-tiles apart;
+//   2. every lane finds its merge-path start by binary search over <= W row_end words in shared memory, then issues
+//      its (up to kIPT) gathers x[src] back to back on the read-only path — values land in REGISTERS in the order
+//      the lane will consume them (no shared-memory round trip);
+//   3. the lane walks its kIPT merge items serially: complete per-vertex reductions go to the warp's sums[] slot,
+//      the leading and trailing partials are stitched across lanes by a segmented warp-shuffle scan (fixed shape ->
+//      deterministic, unlike the reference's float atomicAdd);
+//   4. a lane-strided pass applies the vertex program's update() and stores the new values coalesced — to this GPU's
+//      replica and, in P2P exchange mode, straight into every peer GPU's replica (fused compute + all-gather).
+// A vertex whose in-edge list crosses warp-tile boundaries is finished by the fix-up kernels below: a segmented scan
+// over the tiles' tail partials (fp64 for PageRank) in ascending tile order, independent of the grid size.
 #pragma once
 #include "common.cuh"
 #include "programs.cuh"
 
 namespace luxb {
 
-template <int kThreads_, int kIPT_, int kStages_>
+template <int kIPT_, int kWarps_, int kStages_>
 struct PullShape {
-  static constexpr int kThreads = kThreads_;
-  static constexpr int kIPT = kIPT_;
-  static constexpr int kStages = kStages_;
-  static constexpr int kTile = kThreads * kIPT;
-  static constexpr int kAElems = kTile + 4;  // u64 row_end entries per stage (alignment slack + peek)
-  static constexpr int kEElems = kTile + 8;  // u32 source ids per stage (alignment slack)
-  static constexpr int kWarps = kThreads / 32;
-  static constexpr size_t kStageBytes = (size_t)kAElems * 8 + (size_t)kEElems * 4;
-  static constexpr size_t kSmemBytes = kStages * kStageBytes + (size_t)(kTile + 4) * 4 /*sums*/ + 64 /*scan*/ * 4 +
-                                       kStages * 8 /*mbarriers*/ + 16;
-  static_assert(kIPT % 2 == 1, "kIPT must be odd: thread-contiguous smem walks are then bank-conflict free");
-  static_assert(kThreads % 32 == 0 && kWarps <= 16, "");
+  static constexpr int kIPT = kIPT_;            // merge items per lane
+  static constexpr int kWarps = kWarps_;        // consumer warps per CTA (+1 producer warp)
+  static constexpr int kThreads = 32 * (kWarps + 1);
+  static constexpr int kTile = 32 * kIPT;       // merge items per warp tile
+  static constexpr int kSuper = kTile * kWarps; // merge items per super-tile (one TMA pair)
+  static constexpr int kStages = kStages_;      // ring depth
+  static constexpr int kAElems = kSuper + 8;    // u32 low words of row_end (alignment slack + peek entry)
+  static constexpr int kEElems = kSuper + 8;    // u32 source ids (alignment slack)
+  static constexpr int kSumElems = kTile + 4;   // per consumer warp
+  static constexpr int kHdrElems = kWarps + 4;  // per stage: super-tile id + tile_v[t0 .. t0 + kWarps]
+  static constexpr size_t kSmemBytes = (size_t)kStages * (kAElems + kEElems) * 4 + (size_t)kWarps * kSumElems * 4 +
+                                       2 * kStages * 8 + (size_t)kStages * kHdrElems * 4 + 16;
+  static_assert(kIPT % 2 == 1, "kIPT must be odd: lane-contiguous smem reads are then bank-conflict free");
 };
 
 template <class Prog>
 struct PullArgs {
   const uint64_t* row_end;   // [nPart + 4] end offsets relative to the partition's first edge; padded with ~0
-  const uint32_t* src;       // [ePart + 8] source vertex ids (global)
+  const uint32_t* row_end32; // [nPart + 8] low 32 bits of row_end: what the tile kernel streams (differences inside
+                             // a tile are < 2^32, so tile-relative offsets are exact modulo 2^32)
+  const uint32_t* src;       // [ePart + 8] gather indices of the in-edges' sources (global ids, or hot-packed ids)
   const uint32_t* tile_v;    // [nTiles + 1] merge-path split: vertices consumed before each tile
   uint32_t n_part;           // vertices in this partition
   uint64_t e_part;           // edges in this partition
   uint32_t n_tiles;
   uint32_t row_left;         // global id of local vertex 0
-  const typename Prog::Vertex* x_old;  // [nv] replica of last iteration's values (global index)
+  const typename Prog::Vertex* x_old;  // gather base: last iteration's values, indexed by the ids in `src`
+  const typename Prog::Vertex* x_nat;  // [nv] the same values in natural (global id) order, for update()'s old value
   typename Prog::Vertex* out;          // [nPart] this partition's new values (local index)
-  typename Prog::Acc* head_partial;    // [nTiles]
-  typename Prog::Acc* tail_partial;    // [nTiles]
+  typename Prog::Acc* head_partial;    // [nTiles] reduction of the tile's first completed vertex (tile-local part)
+  typename Prog::Acc* tail_partial;    // [nTiles] reduction of the edges after the tile's last completed vertex
+  typename Prog::Wide* carry;          // [nTiles] fix-up scratch: exclusive in-block carry
+  uint32_t* carry_flag;                // [nTiles]
+  typename Prog::Wide* block_agg;      // [nBlocks] fix-up scratch
+  uint32_t* block_flag;                // [nBlocks]
+  uint32_t* tile_counter;              // dynamic super-tile scheduler (zeroed before every launch)
   typename Prog::Params prm;
   int n_peers;                                        // P2P exchange: peers' slice pointers (local index)
   typename Prog::Vertex* peer_out[LUXB_MAX_PEERS];
@@ -70,187 +86,293 @@ __global__ void tile_table_kernel(const uint64_t* __restrict__ row_end, uint32_t
   tile_v[t] = (uint32_t)lo;
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 template <class Prog, class Shape>
 __global__ void __launch_bounds__(Shape::kThreads) pull_tile_kernel(const __grid_constant__ PullArgs<Prog> a) {
   using Acc = typename Prog::Acc;
   using Vertex = typename Prog::Vertex;
   static_assert(sizeof(Acc) == 4 && sizeof(Vertex) == 4, "4-byte vertex values");
-  constexpr int kThreads = Shape::kThreads, kIPT = Shape::kIPT, kStages = Shape::kStages, kTile = Shape::kTile;
+  constexpr int kIPT = Shape::kIPT, kTile = Shape::kTile, kStages = Shape::kStages, kWarps = Shape::kWarps;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t* a_buf = reinterpret_cast<uint64_t*>(smem_raw);                                         // kStages x kAElems
-  uint32_t* e_buf = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kStages * Shape::kAElems * 8);  // kStages x kEElems
-  Acc* sums = reinterpret_cast<Acc*>(e_buf + (size_t)kStages * Shape::kEElems);                    // kTile + 4
-  Acc* scan_v = sums + (kTile + 4);                                                                // 32
-  uint32_t* scan_f = reinterpret_cast<uint32_t*>(scan_v + 32);                                     // 32
-  uint64_t* full = reinterpret_cast<uint64_t*>(scan_f + 32);                                       // kStages
+  uint32_t* a_buf = reinterpret_cast<uint32_t*>(smem_raw);                       // kStages x kAElems
+  uint32_t* e_buf = a_buf + (size_t)kStages * Shape::kAElems;                    // kStages x kEElems
+  Acc* sums_all = reinterpret_cast<Acc*>(e_buf + (size_t)kStages * Shape::kEElems);  // kWarps x kSumElems
+  uint64_t* full = reinterpret_cast<uint64_t*>(sums_all + (size_t)kWarps * Shape::kSumElems);
+  uint64_t* empty = full + kStages;
+  uint32_t* hdr_all = reinterpret_cast<uint32_t*>(empty + kStages);              // kStages x kHdrElems
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint64_t total = (uint64_t)a.n_part + a.e_part;
-  const uint64_t policy = l2_policy_evict_first();
+  const uint32_t n_super = (a.n_tiles + kWarps - 1) / kWarps;
 
-  if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kWarps); }
     fence_mbar_init();
   }
-  __syncthreads();
+  __syncthreads();  // the only CTA-wide barrier: mbarrier initialisation
 
-  auto issue = [&](uint32_t t, int s) {  // called by thread 0 only
-    uint32_t i0 = __ldg(a.tile_v + t), i1 = __ldg(a.tile_v + t + 1);
-    uint64_t d0 = (uint64_t)t * kTile, d1 = d0 + kTile < total ? d0 + kTile : total;
-    uint64_t j0 = d0 - i0, j1 = d1 - i1;
-    uint32_t is = i0 & ~1u;
-    uint32_t bytes_a = ((i1 - is + 1) * 8 + 15) & ~15u;
-    uint64_t js = j0 & ~3ull;
-    uint32_t bytes_e = (uint32_t)(((j1 - js) * 4 + 15) & ~15ull);
-    if (j1 == j0) bytes_e = 0;
-    mbar_arrive_expect_tx(&full[s], bytes_a + bytes_e);
-    bulk_g2s(a_buf + (size_t)s * Shape::kAElems, a.row_end + is, bytes_a, &full[s], policy);
-    if (bytes_e) bulk_g2s(e_buf + (size_t)s * Shape::kEElems, a.src + js, bytes_e, &full[s], policy);
-  };
-
-  if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      uint64_t t = (uint64_t)blockIdx.x + (uint64_t)s * gridDim.x;
-      if (t < a.n_tiles) issue((uint32_t)t, s);
+  if (warp == kWarps) {
+    // ===== producer warp: claims super-tiles from a global counter (dynamic schedule keeps every CTA inside one
+    // narrow window of the streamed arrays: few live DRAM pages / TLB entries, no tail imbalance), publishes the
+    // tile geometry in the stage header and streams the slices with two TMA bulk copies =====
+    const uint64_t policy = l2_policy_evict_first();
+    for (uint32_t n = 0;; ++n) {
+      const int s = n % kStages;
+      if (n >= (uint32_t)kStages) mbar_wait(&empty[s], ((n / kStages) - 1) & 1u);
+      uint32_t T = 0;
+      if (lane == 0) T = atomicAdd(a.tile_counter, 1u);
+      T = __shfl_sync(0xffffffffu, T, 0);
+      uint32_t* hdr = hdr_all + s * Shape::kHdrElems;
+      if (T >= n_super) {
+        if (lane == 0) { hdr[0] = 0xFFFFFFFFu; mbar_arrive(&full[s]); }
+        break;
+      }
+      const uint64_t t0 = (uint64_t)T * kWarps;
+      if (lane <= kWarps) {
+        uint64_t tt = t0 + lane < a.n_tiles ? t0 + lane : a.n_tiles;
+        hdr[1 + lane] = __ldg(a.tile_v + tt);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        hdr[0] = T;
+        const uint64_t t1 = t0 + kWarps < a.n_tiles ? t0 + kWarps : a.n_tiles;
+        const uint32_t i0 = hdr[1], i1 = hdr[1 + kWarps];
+        const uint64_t d0 = t0 * kTile, d1 = t1 * kTile < total ? t1 * kTile : total;
+        const uint64_t j0 = d0 - i0, j1 = d1 - i1;
+        const uint32_t is = i0 & ~3u;
+        const uint32_t bytes_a = ((i1 - is + 1) * 4 + 15) & ~15u;
+        const uint64_t js = j0 & ~3ull;
+        uint32_t bytes_e = (uint32_t)(((j1 - js) * 4 + 15) & ~15ull);
+        if (j1 == j0) bytes_e = 0;
+        mbar_arrive_expect_tx(&full[s], bytes_a + bytes_e);
+        bulk_g2s(a_buf + (size_t)s * Shape::kAElems, a.row_end32 + is, bytes_a, &full[s], policy);
+        if (bytes_e) bulk_g2s(e_buf + (size_t)s * Shape::kEElems, a.src + js, bytes_e, &full[s], policy);
+      }
+      __syncwarp();
     }
+    return;
   }
 
-  uint32_t n = 0;
-  for (uint64_t t64 = blockIdx.x; t64 < a.n_tiles; t64 += gridDim.x, ++n) {
-    const uint32_t t = (uint32_t)t64;
+  // ===== consumer warps =====
+  Acc* sums = sums_all + (size_t)warp * Shape::kSumElems;
+  for (uint32_t n = 0;; ++n) {
     const int s = n % kStages;
-    const uint32_t parity = (n / kStages) & 1u;
-    const uint32_t i0 = __ldg(a.tile_v + t), i1 = __ldg(a.tile_v + t + 1);
+    mbar_wait(&full[s], (n / kStages) & 1u);
+    const uint32_t* hdr = hdr_all + s * Shape::kHdrElems;
+    const uint32_t T = hdr[0];
+    if (T == 0xFFFFFFFFu) break;
+    const uint64_t t0 = (uint64_t)T * kWarps;
+    const uint64_t t64 = t0 + warp;
+    const bool active = t64 < a.n_tiles;
+    const uint32_t t = (uint32_t)t64;
+    const uint32_t si0 = hdr[1];
+    const uint32_t i0 = hdr[1 + warp], i1 = hdr[2 + warp];
+    const uint64_t sj0 = t0 * kTile - si0;
     const uint64_t d0 = (uint64_t)t * kTile, d1 = d0 + kTile < total ? d0 + kTile : total;
     const uint64_t j0 = d0 - i0, j1 = d1 - i1;
-    const uint32_t n_v = i1 - i0, n_e = (uint32_t)(j1 - j0), n_items = n_v + n_e;
-    const uint64_t* A = a_buf + (size_t)s * Shape::kAElems + (i0 & 1u);
-    uint32_t* E = e_buf + (size_t)s * Shape::kEElems + (uint32_t)(j0 & 3ull);
-    Acc* vals = reinterpret_cast<Acc*>(E);
+    const uint32_t n_v = i1 - i0, n_e = active ? (uint32_t)(j1 - j0) : 0u, n_items = n_v + n_e, j0lo = (uint32_t)j0;
+    const uint32_t* A = a_buf + (size_t)s * Shape::kAElems + (si0 & 3u) + (i0 - si0);
+    const uint32_t* E = e_buf + (size_t)s * Shape::kEElems + (uint32_t)(sj0 & 3ull) + (uint32_t)(j0 - sj0);
 
-    mbar_wait(&full[s], parity);
+    if (active) {
+      // ---- merge-path start of this lane: (i, j) with i + j = lane * kIPT ----
+      uint32_t d = lane * kIPT;
+      if (d > n_items) d = n_items;
+      uint32_t lo = d > n_e ? d - n_e : 0, hi = d < n_v ? d : n_v;
+      while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (A[mid] - j0lo <= d - 1 - mid) lo = mid + 1; else hi = mid;
+      }
+      uint32_t i = lo;
+      const uint32_t j = d - lo;
+      uint32_t i_next = __shfl_down_sync(0xffffffffu, i, 1);
+      uint32_t j_next = __shfl_down_sync(0xffffffffu, j, 1);
+      if (lane == 31) { i_next = n_v; j_next = n_e; }
+      const uint32_t ne_lane = j_next - j;
 
-    // ---- phase 1: gather (compute()): contributions of the tile's in-edges, kIPT loads in flight per thread ----
-    {
+      // ---- gather (compute()): up to kIPT independent read-only loads, parked in registers in walk order ----
       Acc val[kIPT];
 #pragma unroll
-      for (int k = 0; k < kIPT; ++k) {
-        uint32_t idx = tid + k * kThreads;
-        if (idx < n_e) val[k] = Prog::gather(__ldg(a.x_old + E[idx]));
-      }
-#pragma unroll
-      for (int k = 0; k < kIPT; ++k) {
-        uint32_t idx = tid + k * kThreads;
-        if (idx < n_e) vals[idx] = val[k];
-      }
-    }
-    __syncthreads();
+      for (int k = 0; k < kIPT; ++k)
+        if (k < (int)ne_lane) val[k] = Prog::gather(__ldg(a.x_old + E[j + k]));
 
-    // ---- phase 2: serial merge walk over kIPT items per thread ----
-    uint32_t d = tid * kIPT;
-    if (d > n_items) d = n_items;
-    uint32_t dend = d + kIPT < n_items ? d + kIPT : n_items;
-    uint32_t lo = d > n_e ? d - n_e : 0, hi = d < n_v ? d : n_v;
-    while (lo < hi) {
-      uint32_t mid = (lo + hi) >> 1;
-      if (A[mid] <= j0 + (d - 1 - mid)) lo = mid + 1; else hi = mid;
-    }
-    uint32_t i = lo, j = d - lo;
-    Acc acc = Prog::identity();
-    bool has_c = false;
-    uint32_t first_i = 0;
-    Acc first_val = Prog::identity();
-    uint64_t aend = A[i];
+      // ---- serial walk: edges [j, j_next) merged with vertex-end markers [i, i_next) ----
+      Acc acc = Prog::identity();
+      bool has_c = false;
+      uint32_t first_i = 0;
+      Acc first_val = Prog::identity();
+      uint32_t aend = A[i] - j0lo;  // tile-relative end offset of vertex i (i == n_v reads a peek entry, never used)
 #pragma unroll
-    for (int k = 0; k < kIPT; ++k) {
-      if (d + k < dend) {
-        if (aend <= j0 + j) {  // vertex i has no more in-edges: its reduction is complete
-          if (!has_c) { has_c = true; first_i = i; first_val = acc; } else { sums[i] = acc; }
-          acc = Prog::identity();
-          ++i;
-          aend = A[i];
-        } else {
-          acc = Prog::combine(acc, vals[j]);
-          ++j;
+      for (int k = 0; k < kIPT; ++k) {
+        if (k < (int)ne_lane) {
+          while (i < i_next && aend <= j + k) {  // vertex i has no more in-edges: its reduction is complete
+            if (!has_c) { has_c = true; first_i = i; first_val = acc; } else { sums[i] = acc; }
+            acc = Prog::identity();
+            ++i;
+            aend = A[i] - j0lo;
+          }
+          acc = Prog::combine(acc, val[k]);
         }
       }
-    }
-    // segmented inclusive scan of (has_c, trailing partial) over threads: warp shuffles, then one smem hop
-    Acc sv = acc;
-    uint32_t sf = has_c ? 1u : 0u;
+      while (i < i_next) {  // markers after the lane's last edge
+        if (!has_c) { has_c = true; first_i = i; first_val = acc; } else { sums[i] = acc; }
+        acc = Prog::identity();
+        ++i;
+      }
+      // ---- segmented inclusive scan of (has_c, trailing partial) across the warp ----
+      Acc sv = acc;
+      uint32_t sf = has_c ? 1u : 0u;
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      Acc pv = __shfl_up_sync(0xffffffffu, sv, off);
-      uint32_t pf = __shfl_up_sync(0xffffffffu, sf, off);
-      if (lane >= off) {
-        if (!sf) sv = Prog::combine(pv, sv);
-        sf |= pf;
+      for (int off = 1; off < 32; off <<= 1) {
+        Acc pv = __shfl_up_sync(0xffffffffu, sv, off);
+        uint32_t pf = __shfl_up_sync(0xffffffffu, sf, off);
+        if (lane >= off) {
+          if (!sf) sv = Prog::combine(pv, sv);
+          sf |= pf;
+        }
       }
-    }
-    Acc ex_v = __shfl_up_sync(0xffffffffu, sv, 1);
-    uint32_t ex_f = __shfl_up_sync(0xffffffffu, sf, 1);
-    if (lane == 0) { ex_v = Prog::identity(); ex_f = 0; }
-    if (lane == 31) { scan_v[warp] = sv; scan_f[warp] = sf; }
-    fence_proxy_async_smem();
-    __syncthreads();  // all generic accesses to this stage's buffers are done -> stage can be refilled
-    if (tid == 0) {
-      uint64_t tn = t64 + (uint64_t)kStages * gridDim.x;
-      if (tn < a.n_tiles) issue((uint32_t)tn, s);
-    }
-    {
-      Acc pv = Prog::identity();
-      uint32_t pf = 0;
-      for (int w = 0; w < warp; ++w) {
-        if (scan_f[w]) { pv = scan_v[w]; pf = 1; } else { pv = Prog::combine(pv, scan_v[w]); }
+      Acc ex_v = __shfl_up_sync(0xffffffffu, sv, 1);
+      if (lane == 0) ex_v = Prog::identity();
+      if (has_c) sums[first_i] = Prog::combine(ex_v, first_val);
+      const Acc tail = __shfl_sync(0xffffffffu, sv, 31);
+      __syncwarp();  // sums[] complete; every lane is done with this stage's A/E words
+      if (lane == 0) {
+        mbar_arrive(&empty[s]);  // release the ring slot to the producer
+        a.tail_partial[t] = tail;
+        if (n_v > 0) a.head_partial[t] = sums[0];
       }
-      if (!ex_f) ex_v = Prog::combine(pv, ex_v);
-      ex_f |= pf;
-    }
-    if (has_c) sums[first_i] = Prog::combine(ex_v, first_val);
-    Acc tail = Prog::identity();
-    if (tid == 0) {
-      for (int w = 0; w < Shape::kWarps; ++w) {
-        if (scan_f[w]) tail = scan_v[w]; else tail = Prog::combine(tail, scan_v[w]);
+      // ---- update() + coalesced stores (own replica and, in P2P mode, every peer's replica) ----
+      for (uint32_t li = lane; li < n_v; li += 32) {
+        if (li == 0 && t != 0) continue;  // may continue from previous tiles: finished by the fix-up kernels
+        uint32_t v = i0 + li;
+        Vertex oldv = Prog::kNeedsOld ? __ldg(a.x_nat + a.row_left + v) : Vertex();
+        Vertex nv_ = Prog::update(a.row_left + v, sums[li], oldv, a.prm);
+        a.out[v] = nv_;
+        for (int p = 0; p < a.n_peers; ++p) a.peer_out[p][v] = nv_;
       }
+      __syncwarp();  // sums[] reads done before the next tile's walk writes it
+    } else {
+      if (lane == 0) mbar_arrive(&empty[s]);
     }
-    __syncthreads();  // sums[] complete
-
-    // ---- phase 3: update() + coalesced stores (own replica and, in P2P mode, every peer's replica) ----
-    if (tid == 0) {
-      a.tail_partial[t] = tail;
-      if (n_v > 0) a.head_partial[t] = sums[0];
-    }
-    for (uint32_t li = tid; li < n_v; li += kThreads) {
-      if (li == 0 && t != 0) continue;  // may continue from previous tiles: finished by pull_fixup_kernel
-      uint32_t v = i0 + li;
-      Vertex oldv = Prog::kNeedsOld ? __ldg(a.x_old + a.row_left + v) : Vertex();
-      Vertex nv_ = Prog::update(a.row_left + v, sums[li], oldv, a.prm);
-      a.out[v] = nv_;
-      for (int p = 0; p < a.n_peers; ++p) a.peer_out[p][v] = nv_;
-    }
-    // next tile's post-gather __syncthreads orders these sums[] reads before its merge-phase writes
   }
 }
 
-// One thread per tile t >= 1 that completes at least one vertex: local vertex tile_v[t] may have started in earlier
-// tiles.  Combine their tail partials in ascending tile order with this tile's head partial, then update().
+// ---- fix-up: vertices whose in-edge list spans several warp tiles ----------------------------------------------
+// carry into tile t = combination, in ascending tile order, of the tail partials of the tiles since (and including)
+// the last tile before t that completed a vertex.  A segmented scan in three small kernels:
+//   1. per block of kFixBlock tiles: exclusive in-block scan -> carry[t], carry_flag[t]; block aggregate
+//   2. one CTA scans the block aggregates (exclusive)
+//   3. per tile that completes a vertex: total = carry (+ block prefix if no flagged tile precedes it in its block)
+//      + head_partial[t]; update(); store.
+constexpr int kFixBlock = 256;
+
 template <class Prog>
-__global__ void pull_fixup_kernel(const __grid_constant__ PullArgs<Prog> a) {
+__device__ __forceinline__ void seg_combine(uint32_t& f2, typename Prog::Wide& v2, uint32_t f1, typename Prog::Wide v1) {
+  // (f1,v1) earlier, (f2,v2) later
+  if (!f2) v2 = Prog::wcombine(v1, v2);
+  f2 |= f1;
+}
+
+template <class Prog>
+__global__ void __launch_bounds__(kFixBlock) pull_fixup_scan_kernel(const __grid_constant__ PullArgs<Prog> a) {
   using Wide = typename Prog::Wide;
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x + 1;
-  if (t >= a.n_tiles) return;
-  uint32_t i0 = a.tile_v[t], i1 = a.tile_v[t + 1];
+  __shared__ Wide s_v[kFixBlock / 32];
+  __shared__ uint32_t s_f[kFixBlock / 32];
+  const uint32_t t = blockIdx.x * kFixBlock + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t f = 0;
+  Wide v = Prog::widen(Prog::identity());
+  if (t < a.n_tiles) {
+    f = a.tile_v[t + 1] > a.tile_v[t] ? 1u : 0u;
+    v = Prog::widen(a.tail_partial[t]);
+  }
+  Wide sv = v;
+  uint32_t sf = f;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    Wide pv = __shfl_up_sync(0xffffffffu, sv, off);
+    uint32_t pf = __shfl_up_sync(0xffffffffu, sf, off);
+    if (lane >= off) seg_combine<Prog>(sf, sv, pf, pv);
+  }
+  if (lane == 31) { s_v[warp] = sv; s_f[warp] = sf; }
+  __syncthreads();
+  Wide wv = Prog::widen(Prog::identity());
+  uint32_t wf = 0;
+  for (int w = 0; w < warp; ++w) {  // (wf,wv) = aggregate of the preceding warps
+    uint32_t f2 = s_f[w];
+    Wide v2 = s_v[w];
+    seg_combine<Prog>(f2, v2, wf, wv);
+    wf = f2; wv = v2;
+  }
+  Wide ev = __shfl_up_sync(0xffffffffu, sv, 1);
+  uint32_t ef = __shfl_up_sync(0xffffffffu, sf, 1);
+  if (lane == 0) { ev = Prog::widen(Prog::identity()); ef = 0; }
+  seg_combine<Prog>(ef, ev, wf, wv);
+  if (t < a.n_tiles) { a.carry[t] = ev; a.carry_flag[t] = ef; }
+  if (threadIdx.x == kFixBlock - 1) {
+    uint32_t bf = sf;
+    Wide bv = sv;
+    seg_combine<Prog>(bf, bv, wf, wv);
+    a.block_agg[blockIdx.x] = bv;
+    a.block_flag[blockIdx.x] = bf;
+  }
+}
+
+// exclusive scan of the block aggregates, in place, by one CTA (serial chunks + one smem pass)
+template <class Prog>
+__global__ void __launch_bounds__(1024) pull_fixup_blocks_kernel(const __grid_constant__ PullArgs<Prog> a, uint32_t n_blocks) {
+  using Wide = typename Prog::Wide;
+  __shared__ Wide s_v[1024];
+  __shared__ uint32_t s_f[1024];
+  const uint32_t per = (n_blocks + 1023) / 1024;
+  const uint32_t b0 = threadIdx.x * per < n_blocks ? threadIdx.x * per : n_blocks;
+  const uint32_t b1 = b0 + per < n_blocks ? b0 + per : n_blocks;
+  Wide cv = Prog::widen(Prog::identity());
+  uint32_t cf = 0;
+  for (uint32_t b = b0; b < b1; ++b) {
+    uint32_t f2 = a.block_flag[b];
+    Wide v2 = a.block_agg[b];
+    seg_combine<Prog>(f2, v2, cf, cv);
+    cf = f2; cv = v2;
+  }
+  s_v[threadIdx.x] = cv;
+  s_f[threadIdx.x] = cf;
+  __syncthreads();
+  Wide pv = Prog::widen(Prog::identity());
+  uint32_t pf = 0;
+  for (uint32_t k = 0; k < threadIdx.x; ++k) {
+    uint32_t f2 = s_f[k];
+    Wide v2 = s_v[k];
+    seg_combine<Prog>(f2, v2, pf, pv);
+    pf = f2; pv = v2;
+  }
+  for (uint32_t b = b0; b < b1; ++b) {  // rewrite aggregates as exclusive prefixes
+    uint32_t f2 = a.block_flag[b];
+    Wide v2 = a.block_agg[b];
+    a.block_agg[b] = pv;
+    a.block_flag[b] = pf;
+    seg_combine<Prog>(f2, v2, pf, pv);
+    pf = f2; pv = v2;
+  }
+}
+
+template <class Prog>
+__global__ void __launch_bounds__(kFixBlock) pull_fixup_apply_kernel(const __grid_constant__ PullArgs<Prog> a) {
+  using Wide = typename Prog::Wide;
+  const uint32_t t = blockIdx.x * kFixBlock + threadIdx.x;
+  if (t == 0 || t >= a.n_tiles) return;
+  const uint32_t i0 = a.tile_v[t], i1 = a.tile_v[t + 1];
   if (i1 == i0) return;
-  // walk back to the tile in which vertex i0's edge list starts
-  uint32_t s = t - 1;
-  while (s > 0 && a.tile_v[s + 1] == a.tile_v[s]) --s;
-  Wide acc = Prog::widen(Prog::identity());
-  for (uint32_t q = s; q < t; ++q) acc = Prog::wcombine(acc, Prog::widen(a.tail_partial[q]));
-  acc = Prog::wcombine(acc, Prog::widen(a.head_partial[t]));
-  uint32_t v = i0;
-  typename Prog::Vertex oldv = Prog::kNeedsOld ? a.x_old[a.row_left + v] : typename Prog::Vertex();
-  typename Prog::Vertex nv_ = Prog::update(a.row_left + v, Prog::narrow(acc), oldv, a.prm);
+  Wide c = a.carry[t];
+  if (!a.carry_flag[t]) c = Prog::wcombine(a.block_agg[blockIdx.x], c);
+  Wide totalw = Prog::wcombine(c, Prog::widen(a.head_partial[t]));
+  const uint32_t v = i0;
+  typename Prog::Vertex oldv = Prog::kNeedsOld ? a.x_nat[a.row_left + v] : typename Prog::Vertex();
+  typename Prog::Vertex nv_ = Prog::update(a.row_left + v, Prog::narrow(totalw), oldv, a.prm);
   a.out[v] = nv_;
   for (int p = 0; p < a.n_peers; ++p) a.peer_out[p][v] = nv_;
 }

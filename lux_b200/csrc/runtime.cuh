@@ -26,12 +26,19 @@ struct luxb_graph {
   uint32_t row_left = 0, n_part = 0;
   uint64_t col_left = 0, e_part = 0;
   uint64_t* d_row_end = nullptr;  // [n_part + 4] relative end offsets + sentinels
+  uint32_t* d_row_end32 = nullptr;  // [n_part + 8] low words of d_row_end (streamed by the tile kernel)
+  int pull_shape = 1;
   uint32_t* d_src = nullptr;      // [e_part + 8]
   int32_t* d_weight = nullptr;    // [e_part + 8] (col_filter)
   uint32_t* d_tile_v = nullptr;
   uint32_t n_tiles = 0;
   void* d_head = nullptr;
   void* d_tail = nullptr;
+  void* d_carry = nullptr;        // fix-up scratch (per tile / per block of tiles)
+  uint32_t* d_carry_flag = nullptr;
+  void* d_block_agg = nullptr;
+  uint32_t* d_block_flag = nullptr;
+  uint32_t n_fix_blocks = 0;
 
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
@@ -43,6 +50,10 @@ struct luxb_graph {
   void* d_val[2] = {nullptr, nullptr};  // replicas of the vertex values (labels: only [0])
   int cur = 0;
   size_t vbytes = 4;           // bytes per vertex value
+  // hot-packed gather layout (PageRank): value arrays are Z = [hot copy (hot_n) | natural order (nv)]
+  uint32_t hot_n = 0;
+  uint32_t* d_hot_order = nullptr;   // [hot_n] vertex id held by each hot slot (descending out-degree)
+  uint32_t* d_src_gather = nullptr;  // [e_part + 8] source ids rewritten as indices into Z
   // push apps
   uint32_t* d_cur = nullptr;       // [n_part] working labels of this partition
   uint64_t* d_out_end = nullptr;   // [nv] CSR-by-source end offsets over this partition's edges
@@ -65,6 +76,11 @@ struct luxb_graph {
   bool p2p_ready = false;
   void* peer_val[2][LUXB_MAX_PARTS]{};  // imported replicas of the peers (P2P exchange)
   uint32_t* d_sync = nullptr;
+
+  // optional per-launch timing of the dominant kernel
+  bool kernel_timing = false;
+  std::vector<cudaEvent_t> kt_events;  // pairs
+  size_t kt_used = 0;
 
   // stats / trace
   luxb_stats_t stats{};
