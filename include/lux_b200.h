@@ -161,7 +161,7 @@ int luxb_get_out_degree(luxb_graph* g, luxb_vid* host_out, size_t bytes);
  * hot-packed (packed = 1) layout — the memory-system ceiling the pull kernel is compared against. */
 int luxb_debug_gather_ms(luxb_graph* g, int packed, float* ms_out);
 
-/* Raw device pointers for tooling (bench roofline timing, torch interop); not needed by normal callers. */
+/* Raw device pointers for tooling (bench roofline timing, interop); not needed by normal callers. */
 typedef struct {
   void* values;          /* replica of the current vertex values, nv entries */
   const luxb_eid* row_end; /* this rank's offsets, relative to col_left */
