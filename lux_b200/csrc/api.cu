@@ -587,6 +587,27 @@ static int reset_label_state(luxb_graph* g, bool all_active) {
   return 0;
 }
 
+// Pin the hot copies in L2: persisting access-policy window on the hot buffer for every kernel of this stream,
+// everything else is treated as streaming when it misses.  LUXB_L2_PERSIST=0 disables.
+static int set_l2_persisting_window(luxb_graph* g, void* base, size_t bytes) {
+  if (const char* env = getenv("LUXB_L2_PERSIST")) if (atoi(env) == 0) return 0;
+  int max_persist = 0, max_window = 0;
+  LUXB_CUDA(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, g->cfg.device));
+  LUXB_CUDA(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, g->cfg.device));
+  if (max_persist <= 0 || max_window <= 0) return 0;
+  size_t persist = std::min<size_t>((size_t)max_persist, bytes);
+  LUXB_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist));
+  cudaStreamAttrValue attr{};
+  attr.accessPolicyWindow.base_ptr = base;
+  attr.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)max_window);
+  attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)persist / (double)attr.accessPolicyWindow.num_bytes);
+  attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  LUXB_CUDA(cudaStreamSetAttribute(g->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+  if (g->cfg.verbose) printf("L2 persisting window: %zu bytes (device max persisting %d, max window %d)\n", persist, max_persist, max_window);
+  return 0;
+}
+
 // Choose the hot set (largest out-degrees, at most LUXB_HOT_MB megabytes of values, default 64 MB ~ half of L2) and
 // rewrite this partition's source ids as indices into Z = [hot copy | natural] (see build.cuh).
 static int build_hot_layout(luxb_graph* g) {
@@ -674,11 +695,14 @@ int luxb_init(luxb_graph* g) {
       LUXB_CUDA(cudaGetLastError());
       if (g->P > 1) LUXB_NCCL(nccl().AllReduce(g->d_deg, g->d_deg, g->nv, ncclUint32, ncclSum, g->comm, g->stream));
       LUXB_TRY(build_hot_layout(g));
-      for (int k = 0; k < 2; ++k) LUXB_TRY(dmalloc((float**)&g->d_val[k], (uint64_t)g->hot_n + g->nv));
-      pr_init_kernel<<<grid, 256, 0, g->stream>>>(g->d_deg, g->nv, (float*)g->d_val[0] + g->hot_n);
-      LUXB_CUDA(cudaMemsetAsync(g->d_val[1], 0, ((size_t)g->hot_n + g->nv) * 4, g->stream));
-      if (g->hot_n)
-        hot_refresh_kernel<float><<<grid_for(g->hot_n, 256, grid), 256, 0, g->stream>>>((float*)g->d_val[0], g->d_hot_order, g->hot_n);
+      for (int k = 0; k < 2; ++k) LUXB_TRY(dmalloc((float**)&g->d_val[k], g->nv));
+      pr_init_kernel<<<grid, 256, 0, g->stream>>>(g->d_deg, g->nv, (float*)g->d_val[0]);
+      LUXB_CUDA(cudaMemsetAsync(g->d_val[1], 0, (size_t)g->nv * 4, g->stream));
+      if (g->hot_n) {
+        LUXB_TRY(dmalloc((float**)&g->d_hot, g->hot_n));
+        hot_refresh_kernel<float><<<grid_for(g->hot_n, 256, grid), 256, 0, g->stream>>>((float*)g->d_hot, (const float*)g->d_val[0], g->d_hot_order, g->hot_n);
+        LUXB_TRY(set_l2_persisting_window(g, g->d_hot, (size_t)g->hot_n * 4));
+      }
       LUXB_CUDA(cudaGetLastError());
       break;
     }
@@ -781,7 +805,7 @@ static int launch_pull_shape(luxb_graph* g, const PullArgs<Prog>& a) {
 }
 
 template <class Prog>
-static int launch_pull(luxb_graph* g, const typename Prog::Vertex* x_gather, const typename Prog::Vertex* x_nat,
+static int launch_pull(luxb_graph* g, const typename Prog::Vertex* x_nat, const typename Prog::Vertex* x_hot, uint32_t hot_n,
                        const uint32_t* src_idx, typename Prog::Vertex* out_local, const typename Prog::Params& prm,
                        int out_replica /* -1: no peers */) {
   if (g->n_tiles == 0) return 0;
@@ -795,7 +819,9 @@ static int launch_pull(luxb_graph* g, const typename Prog::Vertex* x_gather, con
   a.e_part = g->e_part;
   a.n_tiles = g->n_tiles;
   a.row_left = g->row_left;
-  a.x_old = x_gather;
+  a.x_old = x_nat;
+  a.x_hot = x_hot;
+  a.hot_n = hot_n;
   a.out = out_local;
   a.head_partial = reinterpret_cast<typename Prog::Acc*>(g->d_head);
   a.tail_partial = reinterpret_cast<typename Prog::Acc*>(g->d_tail);
@@ -810,7 +836,7 @@ static int launch_pull(luxb_graph* g, const typename Prog::Vertex* x_gather, con
   if (out_replica >= 0 && g->p2p_ready && g->cfg.exchange == LUXB_EXCHANGE_P2P) {
     for (int p = 0; p < g->P; ++p) {
       if (p == g->cfg.rank) continue;
-      a.peer_out[a.n_peers++] = reinterpret_cast<typename Prog::Vertex*>(g->peer_val[out_replica][p]) + g->hot_n + g->row_left;
+      a.peer_out[a.n_peers++] = reinterpret_cast<typename Prog::Vertex*>(g->peer_val[out_replica][p]) + g->row_left;
     }
   }
   if (g->kernel_timing) {
@@ -849,16 +875,16 @@ static int pagerank_iteration(luxb_graph* g) {
   PageRankProgram::Params prm;
   prm.init_rank = (1.0f - kAlpha) / (float)g->nv;  // pagerank_gpu.cu:144
   prm.deg = g->d_deg;
-  float* z_old = (float*)g->d_val[g->cur];  // [hot copy | natural]
-  float* z_new = (float*)g->d_val[1 - g->cur];
-  LUXB_TRY(launch_pull<PageRankProgram>(g, z_old, z_old + g->hot_n, g->hot_n ? g->d_src_gather : g->d_src,
-                                        z_new + g->hot_n + g->row_left, prm, 1 - g->cur));
+  float* x_old = (float*)g->d_val[g->cur];
+  float* x_new = (float*)g->d_val[1 - g->cur];
+  LUXB_TRY(launch_pull<PageRankProgram>(g, x_old, (const float*)g->d_hot, g->hot_n, g->hot_n ? g->d_src_gather : g->d_src,
+                                        x_new + g->row_left, prm, 1 - g->cur));
   if (g->P > 1) {
     if (g->p2p_ready && g->cfg.exchange == LUXB_EXCHANGE_P2P) LUXB_TRY(p2p_barrier(g));
-    else LUXB_TRY(allgather_slices(g, z_new + g->hot_n, 4));
+    else LUXB_TRY(allgather_slices(g, x_new, 4));
   }
-  if (g->hot_n) {  // every rank refreshes its hot copies from the (now complete) natural part
-    hot_refresh_kernel<float><<<grid_for(g->hot_n, 256, g->num_sms * 8), 256, 0, g->stream>>>(z_new, g->d_hot_order, g->hot_n);
+  if (g->hot_n) {  // every rank refreshes its hot copies (in place) from the now complete new values
+    hot_refresh_kernel<float><<<grid_for(g->hot_n, 256, g->num_sms * 8), 256, 0, g->stream>>>((float*)g->d_hot, x_new, g->d_hot_order, g->hot_n);
     LUXB_CUDA(cudaGetLastError());
     g->stats.kernel_launches++;
   }
@@ -925,7 +951,7 @@ static int label_iteration(luxb_graph* g) {
 
   if (pull) {
     typename Prog::Params prm{0};
-    LUXB_TRY(launch_pull<Prog>(g, lab, lab, g->d_src, g->d_cur, prm, -1));
+    LUXB_TRY(launch_pull<Prog>(g, lab, lab, 0, g->d_src, g->d_cur, prm, -1));
     g->stats.edges_processed += g->e_part;
     g->stats.pull_iterations++;
   } else if (g->n_part && old_size) {
@@ -1130,7 +1156,6 @@ int luxb_get_values(luxb_graph* g, void* host_out, size_t bytes) {
   LUXB_ARG(bytes == need, "buffer is %zu bytes, vertex values need %zu", bytes, need);
   LUXB_CUDA(cudaSetDevice(g->cfg.device));
   const char* srcp = (const char*)((g->cfg.app == LUXB_CC || g->cfg.app == LUXB_SSSP) ? g->d_val[0] : g->d_val[g->cur]);
-  srcp += (size_t)g->hot_n * g->vbytes;  // natural-order part of Z
   LUXB_CUDA(cudaMemcpyAsync(host_out, srcp, need, cudaMemcpyDeviceToHost, g->stream));
   LUXB_CUDA(cudaStreamSynchronize(g->stream));
   return 0;
@@ -1144,9 +1169,9 @@ int luxb_set_values(luxb_graph* g, const void* host_in, size_t bytes) {
   LUXB_CUDA(cudaSetDevice(g->cfg.device));
   const bool labels = g->cfg.app == LUXB_CC || g->cfg.app == LUXB_SSSP;
   char* dstp = (char*)(labels ? g->d_val[0] : g->d_val[g->cur]);
-  LUXB_CUDA(cudaMemcpyAsync(dstp + (size_t)g->hot_n * g->vbytes, host_in, need, cudaMemcpyHostToDevice, g->stream));
+  LUXB_CUDA(cudaMemcpyAsync(dstp, host_in, need, cudaMemcpyHostToDevice, g->stream));
   if (g->hot_n)
-    hot_refresh_kernel<float><<<grid_for(g->hot_n, 256, g->num_sms * 8), 256, 0, g->stream>>>((float*)dstp, g->d_hot_order, g->hot_n);
+    hot_refresh_kernel<float><<<grid_for(g->hot_n, 256, g->num_sms * 8), 256, 0, g->stream>>>((float*)g->d_hot, (const float*)dstp, g->d_hot_order, g->hot_n);
   if (labels) LUXB_TRY(reset_label_state(g, true));
   LUXB_CUDA(cudaStreamSynchronize(g->stream));
   return 0;
@@ -1208,16 +1233,17 @@ int luxb_get_out_degree(luxb_graph* g, luxb_vid* host_out, size_t bytes) {
 }
 
 // dev tooling: raw gather rate over this partition's (possibly hot-packed) source ids, no reduction structure
-__global__ void debug_gather_kernel(const uint32_t* __restrict__ idx, const float* __restrict__ x, uint64_t m, float* out) {
+__global__ void debug_gather_kernel(const uint32_t* __restrict__ idx, const float* __restrict__ nat, const float* __restrict__ hot,
+                                    uint32_t hot_n, uint64_t m, float* out) {
   float acc = 0.f;
   uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; base < m; base += stride * 8) {
     uint32_t id[8];
     float v[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { uint64_t i = base + k * stride; id[k] = i < m ? __ldg(idx + i) : 0; }
+    for (int k = 0; k < 8; ++k) { uint64_t i = base + k * stride; id[k] = i < m ? __ldg(idx + i) : hot_n; }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = __ldg(x + id[k]);
+    for (int k = 0; k < 8; ++k) v[k] = __ldg(id[k] < hot_n ? hot + id[k] : nat + (id[k] - hot_n));
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc += v[k];
   }
@@ -1227,12 +1253,14 @@ __global__ void debug_gather_kernel(const uint32_t* __restrict__ idx, const floa
 int luxb_debug_gather_ms(luxb_graph* g, int packed, float* ms_out) {
   LUXB_ARG(g && ms_out && g->inited && g->cfg.app == LUXB_PAGERANK, "needs an initialised PageRank graph");
   LUXB_CUDA(cudaSetDevice(g->cfg.device));
-  const uint32_t* idx = (packed && g->hot_n) ? g->d_src_gather : g->d_src;
-  const float* x = (const float*)g->d_val[g->cur] + ((packed && g->hot_n) ? 0 : g->hot_n);
+  const bool use_hot = packed && g->hot_n;
+  const uint32_t* idx = use_hot ? g->d_src_gather : g->d_src;
+  const float* nat = (const float*)g->d_val[g->cur];
+  const uint32_t hn = use_hot ? g->hot_n : 0;
   float best = 1e30f;
   for (int r = 0; r < 4; ++r) {
     LUXB_CUDA(cudaEventRecord(g->ev_begin, g->stream));
-    debug_gather_kernel<<<g->num_sms * 4, 256, 0, g->stream>>>(idx, x, g->e_part, (float*)g->d_head);
+    debug_gather_kernel<<<g->num_sms * 4, 256, 0, g->stream>>>(idx, nat, (const float*)g->d_hot, hn, g->e_part, (float*)g->d_head);
     LUXB_CUDA(cudaEventRecord(g->ev_end, g->stream));
     LUXB_CUDA(cudaStreamSynchronize(g->stream));
     float ms = 0.f;
@@ -1246,7 +1274,7 @@ int luxb_debug_gather_ms(luxb_graph* g, int packed, float* ms_out) {
 int luxb_device_view_get(luxb_graph* g, luxb_device_view* out) {
   LUXB_ARG(g && out, "NULL argument");
   const bool labels = g->cfg.app == LUXB_CC || g->cfg.app == LUXB_SSSP;
-  out->values = g->inited ? (void*)((char*)(labels ? g->d_val[0] : g->d_val[g->cur]) + (size_t)g->hot_n * g->vbytes) : nullptr;
+  out->values = g->inited ? (labels ? g->d_val[0] : g->d_val[g->cur]) : nullptr;
   out->row_end = g->d_row_end;
   out->src = g->d_src;
   out->stream = g->stream;
@@ -1284,7 +1312,7 @@ void luxb_close(luxb_graph* g) {
   void* ptrs[] = {g->d_row_end, g->d_row_end32, g->d_src, g->d_weight, g->d_tile_v, g->d_head, g->d_tail, g->d_deg, g->d_val[0], g->d_val[1],
                   g->d_cur, g->d_out_end, g->d_out_dst, g->d_fq_all, g->d_fq_new, g->d_fq_tmp, g->d_hdr_all, g->d_counters,
                   g->d_chunk_first, g->d_chunk_vtx, g->d_partial, g->d_sync, g->d_hot_order, g->d_src_gather,
-                  g->d_carry, g->d_carry_flag, g->d_block_agg, g->d_block_flag};
+                  g->d_carry, g->d_carry_flag, g->d_block_agg, g->d_block_flag, g->d_hot};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (g->h_hdr) cudaFreeHost(g->h_hdr);

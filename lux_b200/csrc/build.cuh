@@ -240,10 +240,10 @@ __global__ void gather_map_hot_kernel(uint32_t* __restrict__ map, const uint32_t
 __global__ void remap_src_kernel(const uint32_t* __restrict__ src, uint64_t n, const uint32_t* __restrict__ map, uint32_t* __restrict__ out) {
   for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) out[e] = map[src[e]];
 }
-// refresh the hot copies from the natural part: Z[h] = Z[H + order[h]]
+// refresh the hot copies from the natural-order values: hot[h] = nat[order[h]]
 template <class T>
-__global__ void hot_refresh_kernel(T* __restrict__ z, const uint32_t* __restrict__ order, uint32_t H) {
-  for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < H; h += (uint64_t)gridDim.x * blockDim.x) z[h] = z[(uint64_t)H + order[h]];
+__global__ void hot_refresh_kernel(T* __restrict__ hot, const T* __restrict__ nat, const uint32_t* __restrict__ order, uint32_t H) {
+  for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < H; h += (uint64_t)gridDim.x * blockDim.x) hot[h] = nat[order[h]];
 }
 
 // PageRank init: x0[v] = (1/nv)/deg[v], or 1/nv for deg 0  (pagerank_gpu.cu:255-259)

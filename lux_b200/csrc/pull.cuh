@@ -56,7 +56,9 @@ struct PullArgs {
   uint64_t e_part;           // edges in this partition
   uint32_t n_tiles;
   uint32_t row_left;         // global id of local vertex 0
-  const typename Prog::Vertex* x_old;  // gather base: last iteration's values, indexed by the ids in `src`
+  const typename Prog::Vertex* x_old;  // [nv] last iteration's values in natural (global id) order
+  const typename Prog::Vertex* x_hot;  // [hot_n] contiguous copies of the hottest vertices' values (L2-persisting window)
+  uint32_t hot_n;                      // ids < hot_n in `src` index x_hot, the others index x_old at (id - hot_n)
   const typename Prog::Vertex* x_nat;  // [nv] the same values in natural (global id) order, for update()'s old value
   typename Prog::Vertex* out;          // [nPart] this partition's new values (local index)
   typename Prog::Acc* head_partial;    // [nTiles] reduction of the tile's first completed vertex (tile-local part)
@@ -198,7 +200,11 @@ __global__ void __launch_bounds__(Shape::kThreads) pull_tile_kernel(const __grid
       Acc val[kIPT];
 #pragma unroll
       for (int k = 0; k < kIPT; ++k)
-        if (k < (int)ne_lane) val[k] = Prog::gather(__ldg(a.x_old + E[j + k]));
+        if (k < (int)ne_lane) {
+          const uint32_t id = E[j + k];
+          const Vertex* p = id < a.hot_n ? a.x_hot + id : a.x_old + (id - a.hot_n);
+          val[k] = Prog::gather(__ldg(p));
+        }
 
       // ---- serial walk: edges [j, j_next) merged with vertex-end markers [i, i_next) ----
       Acc acc = Prog::identity();

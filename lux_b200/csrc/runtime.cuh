@@ -50,8 +50,9 @@ struct luxb_graph {
   void* d_val[2] = {nullptr, nullptr};  // replicas of the vertex values (labels: only [0])
   int cur = 0;
   size_t vbytes = 4;           // bytes per vertex value
-  // hot-packed gather layout (PageRank): value arrays are Z = [hot copy (hot_n) | natural order (nv)]
+  // hot-packed gather layout (PageRank): hot copies live in d_hot, natural-order values in d_val[0/1]
   uint32_t hot_n = 0;
+  void* d_hot = nullptr;             // [hot_n] hot copies (single buffer: refreshed in place after every iteration)
   uint32_t* d_hot_order = nullptr;   // [hot_n] vertex id held by each hot slot (descending out-degree)
   uint32_t* d_src_gather = nullptr;  // [e_part + 8] source ids rewritten as indices into Z
   // push apps

@@ -39,6 +39,14 @@ typedef uint64_t E_ID;   /* pagerank/app.h:22 */
 
 enum { LO_APP_CC = 1, LO_APP_SSSP = 2 };
 
+void lo_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int lo_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

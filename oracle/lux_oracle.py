@@ -49,6 +49,10 @@ def num_threads():
     return lib().lo_num_threads()
 
 
+def set_num_threads(n):
+    lib().lo_set_num_threads(C.c_int(int(n)))
+
+
 def splitmix64(x):
     return lib().lo_splitmix64(C.c_uint64(x & (2**64 - 1)))
 
