@@ -39,7 +39,8 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=int, default=27, help="RMAT scale (27 = BASELINE config; smaller only for debugging)")
     ap.add_argument("--edge-factor", type=int, default=16)
-    ap.add_argument("--exchange", default="p2p", choices=["nccl", "p2p"])
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "p2p", "p2p_fused"],
+                    help="auto = fused P2P stores up to 4 GPUs (measured best), NCCL at 8")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -198,12 +199,14 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    exchange = L.EXCHANGE_P2P if args.exchange == "p2p" else L.EXCHANGE_NCCL
+    if args.exchange == "auto":
+        args.exchange = "p2p_fused" if world <= 4 else "nccl"
+    exchange = {"p2p": L.EXCHANGE_P2P, "p2p_fused": L.EXCHANGE_P2P_FUSED, "nccl": L.EXCHANGE_NCCL}[args.exchange]
     t_build0 = time.perf_counter()
     g = L.LuxGraph.from_rmat(scale, nv, ne, SEED, rank=rank, nranks=world, device=local, exchange=exchange)
     g.comm_init_torch()
     g.init()
-    if world > 1 and exchange == L.EXCHANGE_P2P:
+    if world > 1 and exchange != L.EXCHANGE_NCCL:
         g.p2p_connect_torch()
     t_build = time.perf_counter() - t_build0
     view = g.device_view()

@@ -54,7 +54,10 @@ typedef enum {
 
 typedef enum {
   LUXB_EXCHANGE_NCCL = 0, /* per-iteration NCCL all-gather (grouped broadcasts of unequal slices) */
-  LUXB_EXCHANGE_P2P = 1   /* kernels store their slice straight into every peer's replica over NVLink */
+  LUXB_EXCHANGE_P2P = 1,  /* after the gather kernel, one copy kernel pushes this rank's slice (and its segment of the
+                             hot copies) into every peer's replica with coalesced 128-bit stores over NVLink */
+  LUXB_EXCHANGE_P2P_FUSED = 2 /* the gather kernel itself stores every new value into every peer's replica (fused
+                             compute + all-gather; wins at 2 GPUs, loses at 8 where per-tile stores are tiny) */
 } luxb_exchange;
 
 /* Whole-graph CSC in caller-owned host memory — the arrays of a .lux file (tools/converter.cc:98-124):

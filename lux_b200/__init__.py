@@ -4,11 +4,11 @@ Host side: a thin ctypes mirror of include/lux_b200.h.  All compute is in lux_b2
 sm_100a CUDA).  There is NO CPU fallback: importing works anywhere (so the ABI can be inspected), but opening a
 graph without the library or without a GPU raises.
 """
-from .binding import (APP_PAGERANK, APP_CC, APP_SSSP, APP_COLFILTER, EXCHANGE_NCCL, EXCHANGE_P2P, DENSE_BITMAP,
+from .binding import (APP_PAGERANK, APP_CC, APP_SSSP, APP_COLFILTER, EXCHANGE_NCCL, EXCHANGE_P2P, EXCHANGE_P2P_FUSED, DENSE_BITMAP,
                       SPARSE_QUEUE, CF_K, LuxError, LuxGraph, load_library, partition_csc, library_path,
                       declared_symbols)
 from .apps import pagerank, components, sssp, colfilter  # noqa: F401
 
-__all__ = ["APP_PAGERANK", "APP_CC", "APP_SSSP", "APP_COLFILTER", "EXCHANGE_NCCL", "EXCHANGE_P2P", "DENSE_BITMAP",
+__all__ = ["APP_PAGERANK", "APP_CC", "APP_SSSP", "APP_COLFILTER", "EXCHANGE_NCCL", "EXCHANGE_P2P", "EXCHANGE_P2P_FUSED", "DENSE_BITMAP",
            "SPARSE_QUEUE", "CF_K", "LuxError", "LuxGraph", "load_library", "partition_csc", "library_path",
            "declared_symbols", "pagerank", "components", "sssp", "colfilter"]

@@ -7,7 +7,7 @@ import numpy as np
 from . import build as _build
 
 APP_PAGERANK, APP_CC, APP_SSSP, APP_COLFILTER = 0, 1, 2, 3
-EXCHANGE_NCCL, EXCHANGE_P2P = 0, 1
+EXCHANGE_NCCL, EXCHANGE_P2P, EXCHANGE_P2P_FUSED = 0, 1, 2
 DENSE_BITMAP, SPARSE_QUEUE = 0x1234567, 0x7654321
 CF_K = 20
 MAX_PARTS = 64

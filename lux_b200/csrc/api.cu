@@ -16,6 +16,39 @@
 #include "runtime.cuh"
 
 using namespace luxb;
+// dev aid: LUXB_PHASE_TIMING=1 prints the mean device time of each phase of a PageRank iteration at luxb_close
+struct PhaseTimer {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> tag;
+  double sum[8] = {0};
+  long cnt = 0;
+  const char* name[8] = {"pull_tile", "fixup", "refresh", "push/exchange", "barrier", "", "", ""};
+};
+static PhaseTimer g_pt;
+static void pt_mark(luxb_graph* g, int tag) {
+  if (!g_pt.on) return;
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, g->stream);
+  g_pt.ev.push_back(e);
+  g_pt.tag.push_back(tag);
+}
+static void pt_flush(luxb_graph* g) {
+  if (!g_pt.on || g_pt.ev.empty()) return;
+  cudaStreamSynchronize(g->stream);
+  for (size_t i = 1; i < g_pt.ev.size(); ++i) {
+    if (g_pt.tag[i] < 0) continue;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, g_pt.ev[i - 1], g_pt.ev[i]);
+    g_pt.sum[g_pt.tag[i]] += ms;
+    if (g_pt.tag[i] == 0) g_pt.cnt++;
+  }
+  for (cudaEvent_t e : g_pt.ev) cudaEventDestroy(e);
+  g_pt.ev.clear();
+  g_pt.tag.clear();
+}
+
 
 // ------------------------------------------------------------------------------------------------------------
 namespace luxb {
@@ -460,6 +493,8 @@ int luxb_comm_init(luxb_graph* g, const char id[LUXB_UNIQUE_ID_BYTES]) {
 
 struct P2PBlob {
   cudaIpcMemHandle_t val[2];
+  cudaIpcMemHandle_t hot;
+  int has_hot;
 };
 
 int luxb_p2p_export(luxb_graph* g, void* blob, size_t* blob_bytes) {
@@ -472,6 +507,7 @@ int luxb_p2p_export(luxb_graph* g, void* blob, size_t* blob_bytes) {
   LUXB_CUDA(cudaSetDevice(g->cfg.device));
   for (int k = 0; k < 2; ++k)
     if (g->d_val[k]) LUXB_CUDA(cudaIpcGetMemHandle(&b.val[k], g->d_val[k]));
+  if (g->d_hot) { LUXB_CUDA(cudaIpcGetMemHandle(&b.hot, g->d_hot)); b.has_hot = 1; }
   memcpy(blob, &b, sizeof(b));
   *blob_bytes = sizeof(P2PBlob);
   return 0;
@@ -486,7 +522,8 @@ int luxb_p2p_import(luxb_graph* g, const void* all_blobs, size_t blob_bytes_each
   LUXB_CUDA(cudaSetDevice(g->cfg.device));
   const P2PBlob* blobs = reinterpret_cast<const P2PBlob*>(all_blobs);
   for (int p = 0; p < g->P; ++p) {
-    if (p == g->cfg.rank) { g->peer_val[0][p] = g->d_val[0]; g->peer_val[1][p] = g->d_val[1]; continue; }
+    if (p == g->cfg.rank) { g->peer_val[0][p] = g->d_val[0]; g->peer_val[1][p] = g->d_val[1]; g->peer_hot[p] = g->d_hot; continue; }
+    if (blobs[p].has_hot) LUXB_CUDA(cudaIpcOpenMemHandle(&g->peer_hot[p], blobs[p].hot, cudaIpcMemLazyEnablePeerAccess));
     for (int k = 0; k < 2; ++k) {
       if (!g->d_val[k]) continue;
       LUXB_CUDA(cudaIpcOpenMemHandle(&g->peer_val[k][p], blobs[p].val[k], cudaIpcMemLazyEnablePeerAccess));
@@ -637,31 +674,40 @@ static int build_hot_layout(luxb_graph* g) {
   }
   if (above == 0 || tau > cap) return 0;
   const uint32_t H = (uint32_t)above;
-  uint32_t *d_keys = nullptr, *d_ids = nullptr, *d_keys2 = nullptr, *d_map = nullptr;
-  unsigned int* d_cursor = nullptr;
+  uint64_t *d_keys = nullptr, *d_keys2 = nullptr;
+  uint32_t *d_ids = nullptr, *d_ids2 = nullptr, *d_map = nullptr;
+  unsigned int* d_cursor = nullptr;  // [0] cursor, [1 .. P] per-owner counts
   LUXB_TRY(dmalloc(&d_keys, H));
   LUXB_TRY(dmalloc(&d_keys2, H));
   LUXB_TRY(dmalloc(&d_ids, H));
+  LUXB_TRY(dmalloc(&d_ids2, H));
   LUXB_TRY(dmalloc(&g->d_hot_order, H));
-  LUXB_TRY(dmalloc(&d_cursor, 1));
-  LUXB_CUDA(cudaMemsetAsync(d_cursor, 0, 4, g->stream));
-  hot_select_kernel<<<grid, 256, 0, g->stream>>>(g->d_deg, g->nv, tau, d_cursor, d_keys, d_ids, H);
+  LUXB_TRY(dmalloc(&d_cursor, 1 + LUXB_MAX_PARTS));
+  LUXB_CUDA(cudaMemsetAsync(d_cursor, 0, 4 * (1 + LUXB_MAX_PARTS), g->stream));
+  PartTable pt{};
+  pt.P = g->P;
+  for (int p = 0; p < g->P; ++p) { pt.rl[p] = g->rl[p]; pt.np[p] = g->np[p]; }
+  hot_select_kernel<<<grid, 256, 0, g->stream>>>(g->d_deg, g->nv, tau, pt, d_cursor, d_cursor + 1, d_keys, d_ids, H);
   LUXB_CUDA(cudaGetLastError());
-  // ids are appended in nondeterministic order: sort by (key, id) = two stable passes (id first, then key)
+  // ids arrive in nondeterministic order: sort by (key, id) = two stable passes (id first, then key)
   size_t tb = 0;
   void* d_tmp = nullptr;
   int vbits = 1;
   while ((1ull << vbits) < (uint64_t)g->nv) ++vbits;
-  LUXB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, d_ids, g->d_hot_order, d_keys, d_keys2, (int)H, 0, vbits, g->stream));
+  LUXB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, d_ids, d_ids2, d_keys, d_keys2, (int)H, 0, vbits, g->stream));
   LUXB_CUDA(cudaMalloc(&d_tmp, tb + 256));
-  LUXB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb, d_ids, g->d_hot_order, d_keys, d_keys2, (int)H, 0, vbits, g->stream));
+  LUXB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb, d_ids, d_ids2, d_keys, d_keys2, (int)H, 0, vbits, g->stream));
   LUXB_CUDA(cudaStreamSynchronize(g->stream));
   LUXB_CUDA(cudaFree(d_tmp));
   tb = 0;
-  LUXB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, d_keys2, d_keys, g->d_hot_order, d_ids, (int)H, 0, 32, g->stream));
+  LUXB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, d_keys2, d_keys, d_ids2, g->d_hot_order, (int)H, 0, 40, g->stream));
   LUXB_CUDA(cudaMalloc(&d_tmp, tb + 256));
-  LUXB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb, d_keys2, d_keys, g->d_hot_order, d_ids, (int)H, 0, 32, g->stream));
-  LUXB_CUDA(cudaMemcpyAsync(g->d_hot_order, d_ids, (size_t)H * 4, cudaMemcpyDeviceToDevice, g->stream));
+  LUXB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb, d_keys2, d_keys, d_ids2, g->d_hot_order, (int)H, 0, 40, g->stream));
+  unsigned int h_cnt[1 + LUXB_MAX_PARTS];
+  LUXB_CUDA(cudaMemcpyAsync(h_cnt, d_cursor, sizeof(h_cnt), cudaMemcpyDeviceToHost, g->stream));
+  LUXB_CUDA(cudaStreamSynchronize(g->stream));
+  g->hot_off[0] = 0;
+  for (int p = 0; p < g->P; ++p) g->hot_off[p + 1] = g->hot_off[p] + h_cnt[1 + p];
   LUXB_TRY(dmalloc(&d_map, g->nv));
   gather_map_init_kernel<<<grid, 256, 0, g->stream>>>(d_map, g->nv, H);
   gather_map_hot_kernel<<<grid, 256, 0, g->stream>>>(d_map, g->d_hot_order, H);
@@ -674,6 +720,7 @@ static int build_hot_layout(luxb_graph* g) {
   LUXB_CUDA(cudaFree(d_keys));
   LUXB_CUDA(cudaFree(d_keys2));
   LUXB_CUDA(cudaFree(d_ids));
+  LUXB_CUDA(cudaFree(d_ids2));
   LUXB_CUDA(cudaFree(d_cursor));
   LUXB_CUDA(cudaFree(d_map));
   g->hot_n = H;
@@ -700,7 +747,7 @@ int luxb_init(luxb_graph* g) {
       LUXB_CUDA(cudaMemsetAsync(g->d_val[1], 0, (size_t)g->nv * 4, g->stream));
       if (g->hot_n) {
         LUXB_TRY(dmalloc((float**)&g->d_hot, g->hot_n));
-        hot_refresh_kernel<float><<<grid_for(g->hot_n, 256, grid), 256, 0, g->stream>>>((float*)g->d_hot, (const float*)g->d_val[0], g->d_hot_order, g->hot_n);
+        hot_refresh_kernel<float><<<grid_for(g->hot_n, 256, grid), 256, 0, g->stream>>>((float*)g->d_hot, (const float*)g->d_val[0], g->d_hot_order, 0, g->hot_n);
         LUXB_TRY(set_l2_persisting_window(g, g->d_hot, (size_t)g->hot_n * 4));
       }
       LUXB_CUDA(cudaGetLastError());
@@ -833,7 +880,7 @@ static int launch_pull(luxb_graph* g, const typename Prog::Vertex* x_nat, const 
   LUXB_CUDA(cudaMemsetAsync(a.tile_counter, 0, 4, g->stream));
   a.prm = prm;
   a.n_peers = 0;
-  if (out_replica >= 0 && g->p2p_ready && g->cfg.exchange == LUXB_EXCHANGE_P2P) {
+  if (out_replica >= 0 && g->p2p_ready && g->cfg.exchange == LUXB_EXCHANGE_P2P_FUSED) {
     for (int p = 0; p < g->P; ++p) {
       if (p == g->cfg.rank) continue;
       a.peer_out[a.n_peers++] = reinterpret_cast<typename Prog::Vertex*>(g->peer_val[out_replica][p]) + g->row_left;
@@ -860,6 +907,7 @@ static int launch_pull(luxb_graph* g, const typename Prog::Vertex* x_nat, const 
     g->kt_used += 2;
   }
   g->stats.kernel_launches++;
+  pt_mark(g, 0);
   if (g->n_tiles > 1) {
     pull_fixup_scan_kernel<Prog><<<g->n_fix_blocks, kFixBlock, 0, g->stream>>>(a);
     pull_fixup_blocks_kernel<Prog><<<1, 1024, 0, g->stream>>>(a, g->n_fix_blocks);
@@ -867,26 +915,64 @@ static int launch_pull(luxb_graph* g, const typename Prog::Vertex* x_nat, const 
     LUXB_CUDA(cudaGetLastError());
     g->stats.kernel_launches += 3;
   }
+  pt_mark(g, 1);
   return 0;
 }
 }  // extern "C++"
 
 static int pagerank_iteration(luxb_graph* g) {
+  static int init = 0;
+  if (!init) { init = 1; const char* env = getenv("LUXB_PHASE_TIMING"); g_pt.on = env && atoi(env) != 0; }
+  pt_mark(g, -1);
   PageRankProgram::Params prm;
   prm.init_rank = (1.0f - kAlpha) / (float)g->nv;  // pagerank_gpu.cu:144
   prm.deg = g->d_deg;
   float* x_old = (float*)g->d_val[g->cur];
   float* x_new = (float*)g->d_val[1 - g->cur];
+  const bool p2p = g->P > 1 && g->p2p_ready && g->cfg.exchange != LUXB_EXCHANGE_NCCL;
+  const bool fused = p2p && g->cfg.exchange == LUXB_EXCHANGE_P2P_FUSED;
   LUXB_TRY(launch_pull<PageRankProgram>(g, x_old, (const float*)g->d_hot, g->hot_n, g->hot_n ? g->d_src_gather : g->d_src,
-                                        x_new + g->row_left, prm, 1 - g->cur));
-  if (g->P > 1) {
-    if (g->p2p_ready && g->cfg.exchange == LUXB_EXCHANGE_P2P) LUXB_TRY(p2p_barrier(g));
+                                        x_new + g->row_left, prm, fused ? 1 - g->cur : -1));
+  const int me = g->cfg.rank;
+  if (p2p && !fused) {
+    // push my natural-order slice into every peer's NEW replica (double-buffered, so peers still gathering from the
+    // old one are not disturbed); the single-buffered hot copies are refreshed only after the barrier
+    static int use_kernel = -1;  // DMA (copy engines) by default; LUXB_P2P_PUSH=kernel uses SM stores
+    if (use_kernel < 0) { const char* env = getenv("LUXB_P2P_PUSH"); use_kernel = (env && !strcmp(env, "kernel")) ? 1 : 0; }
+    PushRegions r{};
+    int peers[LUXB_MAX_PARTS];
+    for (int p = 0; p < g->P; ++p)
+      if (p != me) peers[r.n_peers++] = p;
+    if (g->n_part) {
+      int q = r.n_regions++;
+      r.src[q] = reinterpret_cast<const uint32_t*>(x_new) + g->row_left;
+      r.words[q] = g->n_part;
+      for (int k = 0; k < r.n_peers; ++k) r.dst[q][k] = reinterpret_cast<uint32_t*>(g->peer_val[1 - g->cur][peers[k]]) + g->row_left;
+    }
+    if (use_kernel) {
+      if (r.n_regions && r.n_peers) {
+        p2p_push_kernel<<<g->num_sms * 4, 512, 0, g->stream>>>(r);
+        g->stats.kernel_launches++;
+      }
+    } else {
+      for (int q = 0; q < r.n_regions; ++q)
+        for (int k = 0; k < r.n_peers; ++k)  // start at a different peer on every rank: spreads the ingress load
+          LUXB_CUDA(cudaMemcpyAsync(r.dst[q][(k + me) % r.n_peers], r.src[q], r.words[q] * 4, cudaMemcpyDefault, g->stream));
+    }
+    LUXB_CUDA(cudaGetLastError());
+    pt_mark(g, 3);
+    LUXB_TRY(p2p_barrier(g));
+    pt_mark(g, 4);
+  } else if (g->P > 1) {
+    if (fused) LUXB_TRY(p2p_barrier(g));
     else LUXB_TRY(allgather_slices(g, x_new, 4));
+    pt_mark(g, 3);
   }
   if (g->hot_n) {  // every rank refreshes its hot copies (in place) from the now complete new values
-    hot_refresh_kernel<float><<<grid_for(g->hot_n, 256, g->num_sms * 8), 256, 0, g->stream>>>((float*)g->d_hot, x_new, g->d_hot_order, g->hot_n);
+    hot_refresh_kernel<float><<<grid_for(g->hot_n, 256, g->num_sms * 8), 256, 0, g->stream>>>((float*)g->d_hot, x_new, g->d_hot_order, 0, g->hot_n);
     LUXB_CUDA(cudaGetLastError());
     g->stats.kernel_launches++;
+    pt_mark(g, 2);
   }
   g->cur ^= 1;
   g->stats.edges_processed += g->e_part;
@@ -910,7 +996,7 @@ static int colfilter_iteration(luxb_graph* g) {
     a.partial = g->d_partial;
     a.out = x_new + (size_t)g->row_left * kCfK;
     a.n_peers = 0;
-    if (g->p2p_ready && g->cfg.exchange == LUXB_EXCHANGE_P2P)
+    if (g->p2p_ready && g->cfg.exchange != LUXB_EXCHANGE_NCCL)
       for (int p = 0; p < g->P; ++p)
         if (p != g->cfg.rank) a.peer_out[a.n_peers++] = (float*)g->peer_val[1 - g->cur][p] + (size_t)g->row_left * kCfK;
     uint64_t warps = g->n_chunks;
@@ -921,7 +1007,7 @@ static int colfilter_iteration(luxb_graph* g) {
     g->stats.kernel_launches += 2;
   }
   if (g->P > 1) {
-    if (g->p2p_ready && g->cfg.exchange == LUXB_EXCHANGE_P2P) LUXB_TRY(p2p_barrier(g));
+    if (g->p2p_ready && g->cfg.exchange != LUXB_EXCHANGE_NCCL) LUXB_TRY(p2p_barrier(g));
     else LUXB_TRY(allgather_slices(g, x_new, 4 * kCfK));
   }
   g->cur ^= 1;
@@ -1095,6 +1181,7 @@ static int one_iteration(luxb_graph* g) {
 }
 
 static int finish_timed(luxb_graph* g) {
+  pt_flush(g);
   LUXB_CUDA(cudaEventRecord(g->ev_end, g->stream));
   LUXB_CUDA(cudaStreamSynchronize(g->stream));
   float ms = 0.f;
@@ -1171,7 +1258,7 @@ int luxb_set_values(luxb_graph* g, const void* host_in, size_t bytes) {
   char* dstp = (char*)(labels ? g->d_val[0] : g->d_val[g->cur]);
   LUXB_CUDA(cudaMemcpyAsync(dstp, host_in, need, cudaMemcpyHostToDevice, g->stream));
   if (g->hot_n)
-    hot_refresh_kernel<float><<<grid_for(g->hot_n, 256, g->num_sms * 8), 256, 0, g->stream>>>((float*)g->d_hot, (const float*)dstp, g->d_hot_order, g->hot_n);
+    hot_refresh_kernel<float><<<grid_for(g->hot_n, 256, g->num_sms * 8), 256, 0, g->stream>>>((float*)g->d_hot, (const float*)dstp, g->d_hot_order, 0, g->hot_n);
   if (labels) LUXB_TRY(reset_label_state(g, true));
   LUXB_CUDA(cudaStreamSynchronize(g->stream));
   return 0;
@@ -1301,6 +1388,12 @@ int luxb_get_local_csc(luxb_graph* g, luxb_eid* row_end_abs, luxb_vid* src, int3
 
 void luxb_close(luxb_graph* g) {
   if (!g) return;
+  if (g_pt.on && g_pt.cnt) {
+    fprintf(stderr, "[luxb rank %d] phase means over %ld iterations:", g->cfg.rank, g_pt.cnt);
+    for (int k = 0; k < 5; ++k) fprintf(stderr, " %s %.3f ms;", g_pt.name[k], g_pt.sum[k] / g_pt.cnt);
+    fprintf(stderr, "\n");
+    g_pt = PhaseTimer();
+  }
   cudaSetDevice(g->cfg.device);
   if (g->stream) cudaStreamSynchronize(g->stream);
   if (g->p2p_ready)
@@ -1308,6 +1401,9 @@ void luxb_close(luxb_graph* g) {
       if (p != g->cfg.rank)
         for (int k = 0; k < 2; ++k)
           if (g->peer_val[k][p]) cudaIpcCloseMemHandle(g->peer_val[k][p]);
+  if (g->p2p_ready)
+    for (int p = 0; p < g->P; ++p)
+      if (p != g->cfg.rank && g->peer_hot[p]) cudaIpcCloseMemHandle(g->peer_hot[p]);
   if (g->comm) nccl().CommDestroy(g->comm);
   void* ptrs[] = {g->d_row_end, g->d_row_end32, g->d_src, g->d_weight, g->d_tile_v, g->d_head, g->d_tail, g->d_deg, g->d_val[0], g->d_val[1],
                   g->d_cur, g->d_out_end, g->d_out_dst, g->d_fq_all, g->d_fq_new, g->d_fq_tmp, g->d_hdr_all, g->d_counters,

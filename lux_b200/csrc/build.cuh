@@ -211,9 +211,24 @@ __global__ void degree_hist_kernel(const uint32_t* __restrict__ deg, uint32_t nv
   }
 }
 
-// keys/vals for the hot vertices only (compacted with a warp-aggregated cursor); key ascending = degree descending
-__global__ void hot_select_kernel(const uint32_t* __restrict__ deg, uint32_t nv, uint32_t tau, unsigned int* cursor,
-                                  uint32_t* __restrict__ keys, uint32_t* __restrict__ ids, uint32_t capacity) {
+struct PartTable {
+  uint32_t rl[LUXB_MAX_PARTS];
+  uint32_t np[LUXB_MAX_PARTS];
+  int P;
+};
+__device__ __forceinline__ int owner_of(const PartTable& pt, uint32_t v) {
+  int o = 0;
+  for (int p = 0; p < pt.P; ++p)
+    if (pt.np[p] && v >= pt.rl[p]) o = p;
+  return o;
+}
+
+// keys/ids of the hot vertices only (compacted with a warp-aggregated cursor).  key = owner partition in the high
+// word, inverted out-degree in the low word: ascending key = grouped by owner, hottest first inside each group
+// (each rank can then refresh and push ITS segment of the hot copies as one contiguous slice).
+__global__ void hot_select_kernel(const uint32_t* __restrict__ deg, uint32_t nv, uint32_t tau, PartTable pt, unsigned int* cursor,
+                                  unsigned int* __restrict__ per_owner, uint64_t* __restrict__ keys, uint32_t* __restrict__ ids,
+                                  uint32_t capacity) {
   const unsigned lane = threadIdx.x & 31;
   uint64_t n_round = ((uint64_t)nv + 31) & ~31ull;
   for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_round; v += (uint64_t)gridDim.x * blockDim.x) {
@@ -225,7 +240,9 @@ __global__ void hot_select_kernel(const uint32_t* __restrict__ deg, uint32_t nv,
       base = __shfl_sync(0xffffffffu, base, 0);
       if (hot) {
         unsigned pos = base + __popc(m & ((1u << lane) - 1));
-        if (pos < capacity) { keys[pos] = 0xFFFFFFFFu - deg[v]; ids[pos] = (uint32_t)v; }
+        int o = owner_of(pt, (uint32_t)v);
+        atomicAdd(per_owner + o, 1u);
+        if (pos < capacity) { keys[pos] = ((uint64_t)o << 32) | (0xFFFFFFFFu - deg[v]); ids[pos] = (uint32_t)v; }
       }
     }
   }
@@ -240,10 +257,44 @@ __global__ void gather_map_hot_kernel(uint32_t* __restrict__ map, const uint32_t
 __global__ void remap_src_kernel(const uint32_t* __restrict__ src, uint64_t n, const uint32_t* __restrict__ map, uint32_t* __restrict__ out) {
   for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) out[e] = map[src[e]];
 }
-// refresh the hot copies from the natural-order values: hot[h] = nat[order[h]]
+// refresh hot copies [h0, h1) from the natural-order values: hot[h] = nat[order[h]]
 template <class T>
-__global__ void hot_refresh_kernel(T* __restrict__ hot, const T* __restrict__ nat, const uint32_t* __restrict__ order, uint32_t H) {
-  for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < H; h += (uint64_t)gridDim.x * blockDim.x) hot[h] = nat[order[h]];
+__global__ void hot_refresh_kernel(T* __restrict__ hot, const T* __restrict__ nat, const uint32_t* __restrict__ order, uint32_t h0,
+                                   uint32_t h1) {
+  for (uint64_t h = (uint64_t)h0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < h1; h += (uint64_t)gridDim.x * blockDim.x)
+    hot[h] = nat[order[h]];
+}
+
+// P2P push exchange: copy up to two contiguous regions of this rank's buffers to the same offsets of every peer's
+// buffers with 128-bit stores (NVLink writes; peers' pointers come from cudaIpcOpenMemHandle).
+struct PushRegions {
+  const uint32_t* src[2];
+  uint64_t words[2];
+  uint32_t* dst[2][LUXB_MAX_PARTS];
+  int n_regions, n_peers;
+};
+__global__ void p2p_push_kernel(const __grid_constant__ PushRegions r) {
+  for (int q = 0; q < r.n_regions; ++q) {
+    const uint32_t* s = r.src[q];
+    const uint64_t n = r.words[q];
+    // head up to 16-byte alignment, body as uint4, tail
+    uint64_t head = ((16 - ((uintptr_t)s & 15)) & 15) >> 2;
+    if (head > n) head = n;
+    uint64_t body = (n - head) >> 2;
+    for (int p = 0; p < r.n_peers; ++p) {
+      uint32_t* d = r.dst[q][p];
+      if ((((uintptr_t)d) & 15) != (((uintptr_t)s) & 15)) {  // differently aligned: word copies
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) d[i] = s[i];
+        continue;
+      }
+      for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < head; i += (uint64_t)gridDim.x * blockDim.x) d[i] = s[i];
+      const uint4* s4 = reinterpret_cast<const uint4*>(s + head);
+      uint4* d4 = reinterpret_cast<uint4*>(d + head);
+      for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < body; i += (uint64_t)gridDim.x * blockDim.x) d4[i] = s4[i];
+      for (uint64_t i = head + body * 4 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        d[i] = s[i];
+    }
+  }
 }
 
 // PageRank init: x0[v] = (1/nv)/deg[v], or 1/nv for deg 0  (pagerank_gpu.cu:255-259)

@@ -53,6 +53,7 @@ struct luxb_graph {
   // hot-packed gather layout (PageRank): hot copies live in d_hot, natural-order values in d_val[0/1]
   uint32_t hot_n = 0;
   void* d_hot = nullptr;             // [hot_n] hot copies (single buffer: refreshed in place after every iteration)
+  uint32_t hot_off[LUXB_MAX_PARTS + 1]{};  // hot slots owned by partition p: [hot_off[p], hot_off[p+1])
   uint32_t* d_hot_order = nullptr;   // [hot_n] vertex id held by each hot slot (descending out-degree)
   uint32_t* d_src_gather = nullptr;  // [e_part + 8] source ids rewritten as indices into Z
   // push apps
@@ -76,6 +77,7 @@ struct luxb_graph {
   luxb::ncclComm_t comm = nullptr;
   bool p2p_ready = false;
   void* peer_val[2][LUXB_MAX_PARTS]{};  // imported replicas of the peers (P2P exchange)
+  void* peer_hot[LUXB_MAX_PARTS]{};
   uint32_t* d_sync = nullptr;
 
   // optional per-launch timing of the dominant kernel

@@ -32,14 +32,14 @@ def main():
 
     # ---- partition table must equal the reference greedy split (oracle) on every rank ----
     cnt, rl, rr, cl, _, _ = O.partition(row_end, ne, world)
-    for exchange, ename in ((L.EXCHANGE_NCCL, "nccl"), (L.EXCHANGE_P2P, "p2p")):
+    for exchange, ename in ((L.EXCHANGE_NCCL, "nccl"), (L.EXCHANGE_P2P, "p2p"), (L.EXCHANGE_P2P_FUSED, "p2p_fused")):
         g = L.LuxGraph.from_rmat(scale, nv, ne, seed, rank=rank, nranks=world, device=local, exchange=exchange)
         b = g.bounds()
         report("partition[%s]" % ename, b["found"] == cnt and np.array_equal(b["row_left"], rl) and
                np.array_equal(b["row_right"], rr) and np.array_equal(b["col_left"], cl))
         g.comm_init_torch()
         g.init()
-        if exchange == L.EXCHANGE_P2P:
+        if exchange != L.EXCHANGE_NCCL:
             g.p2p_connect_torch()
         g.iterate(6)
         x = g.values()
