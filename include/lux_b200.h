@@ -54,8 +54,8 @@ typedef enum {
 
 typedef enum {
   LUXB_EXCHANGE_NCCL = 0, /* per-iteration NCCL all-gather (grouped broadcasts of unequal slices) */
-  LUXB_EXCHANGE_P2P = 1,  /* after the gather kernel, one copy kernel pushes this rank's slice (and its segment of the
-                             hot copies) into every peer's replica with coalesced 128-bit stores over NVLink */
+  LUXB_EXCHANGE_P2P = 1,  /* balanced all-gather: each rank DMA-copies the parts of its slice that fall into a peer's
+                             EQUAL chunk into that peer's replica (NVLink), then ncclAllGather of the equal chunks */
   LUXB_EXCHANGE_P2P_FUSED = 2 /* the gather kernel itself stores every new value into every peer's replica (fused
                              compute + all-gather; wins at 2 GPUs, loses at 8 where per-tile stores are tiny) */
 } luxb_exchange;

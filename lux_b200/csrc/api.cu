@@ -742,11 +742,14 @@ int luxb_init(luxb_graph* g) {
       LUXB_CUDA(cudaGetLastError());
       if (g->P > 1) LUXB_NCCL(nccl().AllReduce(g->d_deg, g->d_deg, g->nv, ncclUint32, ncclSum, g->comm, g->stream));
       LUXB_TRY(build_hot_layout(g));
-      for (int k = 0; k < 2; ++k) LUXB_TRY(dmalloc((float**)&g->d_val[k], g->nv));
+      g->ag_chunk = ((uint64_t)g->nv + g->P - 1) / g->P;  // equal chunks of the balanced all-gather
+      g->ag_chunk = (g->ag_chunk + 31) & ~31ull;
+      for (int k = 0; k < 2; ++k) LUXB_TRY(dmalloc((float**)&g->d_val[k], g->ag_chunk * g->P));
       pr_init_kernel<<<grid, 256, 0, g->stream>>>(g->d_deg, g->nv, (float*)g->d_val[0]);
       LUXB_CUDA(cudaMemsetAsync(g->d_val[1], 0, (size_t)g->nv * 4, g->stream));
       if (g->hot_n) {
-        LUXB_TRY(dmalloc((float**)&g->d_hot, g->hot_n));
+        g->hot_chunk = (((uint64_t)g->hot_n + g->P - 1) / g->P + 31) & ~31ull;
+        LUXB_TRY(dmalloc((float**)&g->d_hot, g->hot_chunk * g->P));
         hot_refresh_kernel<float><<<grid_for(g->hot_n, 256, grid), 256, 0, g->stream>>>((float*)g->d_hot, (const float*)g->d_val[0], g->d_hot_order, 0, g->hot_n);
         LUXB_TRY(set_l2_persisting_window(g, g->d_hot, (size_t)g->hot_n * 4));
       }
@@ -935,44 +938,47 @@ static int pagerank_iteration(luxb_graph* g) {
                                         x_new + g->row_left, prm, fused ? 1 - g->cur : -1));
   const int me = g->cfg.rank;
   if (p2p && !fused) {
-    // push my natural-order slice into every peer's NEW replica (double-buffered, so peers still gathering from the
-    // old one are not disturbed); the single-buffered hot copies are refreshed only after the barrier
-    static int use_kernel = -1;  // DMA (copy engines) by default; LUXB_P2P_PUSH=kernel uses SM stores
-    if (use_kernel < 0) { const char* env = getenv("LUXB_P2P_PUSH"); use_kernel = (env && !strcmp(env, "kernel")) ? 1 : 0; }
-    PushRegions r{};
-    int peers[LUXB_MAX_PARTS];
-    for (int p = 0; p < g->P; ++p)
-      if (p != me) peers[r.n_peers++] = p;
-    if (g->n_part) {
-      int q = r.n_regions++;
-      r.src[q] = reinterpret_cast<const uint32_t*>(x_new) + g->row_left;
-      r.words[q] = g->n_part;
-      for (int k = 0; k < r.n_peers; ++k) r.dst[q][k] = reinterpret_cast<uint32_t*>(g->peer_val[1 - g->cur][peers[k]]) + g->row_left;
+    // Balanced all-gather.  Edge-balanced partitions own very different numbers of vertices (RMAT-27 at P = 8:
+    // rank 7 owns ~40 %), so "every owner sends its slice to everyone" is bound by the biggest owner's egress.
+    // Step 1: re-chunk — each rank copies the parts of its slice that fall into peer k's EQUAL chunk
+    //         [k*C, (k+1)*C) straight into k's new replica (DMA over NVLink, at most its own slice once);
+    // Step 2: after a barrier, ncclAllGather of the equal chunks in place (NVLS / ring at full bus bandwidth).
+    const uint64_t C = g->ag_chunk;
+    const uint64_t s0 = g->row_left, s1 = (uint64_t)g->row_left + g->n_part;
+    for (int k = 0; k < g->P; ++k) {
+      if (k == me) continue;
+      uint64_t lo = std::max<uint64_t>(s0, k * C), hi = std::min<uint64_t>(s1, (k + 1) * C);
+      if (lo < hi)
+        LUXB_CUDA(cudaMemcpyAsync(reinterpret_cast<float*>(g->peer_val[1 - g->cur][k]) + lo, x_new + lo, (hi - lo) * 4,
+                                  cudaMemcpyDefault, g->stream));
     }
-    if (use_kernel) {
-      if (r.n_regions && r.n_peers) {
-        p2p_push_kernel<<<g->num_sms * 4, 512, 0, g->stream>>>(r);
-        g->stats.kernel_launches++;
-      }
-    } else {
-      for (int q = 0; q < r.n_regions; ++q)
-        for (int k = 0; k < r.n_peers; ++k)  // start at a different peer on every rank: spreads the ingress load
-          LUXB_CUDA(cudaMemcpyAsync(r.dst[q][(k + me) % r.n_peers], r.src[q], r.words[q] * 4, cudaMemcpyDefault, g->stream));
-    }
-    LUXB_CUDA(cudaGetLastError());
     pt_mark(g, 3);
     LUXB_TRY(p2p_barrier(g));
+    LUXB_NCCL(nccl().AllGather(x_new + me * C, x_new, C, ncclFloat32, g->comm, g->stream));
     pt_mark(g, 4);
-  } else if (g->P > 1) {
-    if (fused) LUXB_TRY(p2p_barrier(g));
-    else LUXB_TRY(allgather_slices(g, x_new, 4));
-    pt_mark(g, 3);
-  }
-  if (g->hot_n) {  // every rank refreshes its hot copies (in place) from the now complete new values
-    hot_refresh_kernel<float><<<grid_for(g->hot_n, 256, g->num_sms * 8), 256, 0, g->stream>>>((float*)g->d_hot, x_new, g->d_hot_order, 0, g->hot_n);
-    LUXB_CUDA(cudaGetLastError());
-    g->stats.kernel_launches++;
-    pt_mark(g, 2);
+    if (g->hot_n) {  // each rank refreshes 1/P of the hot copies, then the hot buffer is all-gathered the same way
+      const uint64_t HC = g->hot_chunk;
+      uint32_t h0 = (uint32_t)std::min<uint64_t>(me * HC, g->hot_n), h1 = (uint32_t)std::min<uint64_t>((me + 1) * HC, g->hot_n);
+      if (h1 > h0) {
+        hot_refresh_kernel<float><<<grid_for(h1 - h0, 256, g->num_sms * 8), 256, 0, g->stream>>>((float*)g->d_hot, x_new, g->d_hot_order, h0, h1);
+        g->stats.kernel_launches++;
+      }
+      LUXB_NCCL(nccl().AllGather((float*)g->d_hot + me * HC, g->d_hot, HC, ncclFloat32, g->comm, g->stream));
+      LUXB_CUDA(cudaGetLastError());
+      pt_mark(g, 2);
+    }
+  } else {
+    if (g->P > 1) {
+      if (fused) LUXB_TRY(p2p_barrier(g));
+      else LUXB_TRY(allgather_slices(g, x_new, 4));
+      pt_mark(g, 3);
+    }
+    if (g->hot_n) {  // every rank refreshes its hot copies (in place) from the now complete new values
+      hot_refresh_kernel<float><<<grid_for(g->hot_n, 256, g->num_sms * 8), 256, 0, g->stream>>>((float*)g->d_hot, x_new, g->d_hot_order, 0, g->hot_n);
+      LUXB_CUDA(cudaGetLastError());
+      g->stats.kernel_launches++;
+      pt_mark(g, 2);
+    }
   }
   g->cur ^= 1;
   g->stats.edges_processed += g->e_part;

@@ -88,6 +88,26 @@ __global__ void tile_table_kernel(const uint64_t* __restrict__ row_end, uint32_t
   tile_v[t] = (uint32_t)lo;
 }
 
+// Read-only gather with an L1 policy: hot copies are worth keeping in L1 (evict_last), a cold value is touched once
+// per sweep and must not push them out (no_allocate).  LUXB_GATHER_HINTS=0 at compile time restores plain __ldg.
+#ifndef LUXB_GATHER_HINTS
+#define LUXB_GATHER_HINTS 1
+#endif
+template <class T>
+__device__ __forceinline__ T gather_load(const T* p, bool hot) {
+#if LUXB_GATHER_HINTS
+  uint32_t v;
+  if (hot) asm volatile("ld.global.nc.L1::evict_last.b32 %0, [%1];" : "=r"(v) : "l"(p));
+  else asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(p));
+  T r;
+  memcpy(&r, &v, 4);
+  return r;
+#else
+  (void)hot;
+  return __ldg(p);
+#endif
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -202,8 +222,9 @@ __global__ void __launch_bounds__(Shape::kThreads) pull_tile_kernel(const __grid
       for (int k = 0; k < kIPT; ++k)
         if (k < (int)ne_lane) {
           const uint32_t id = E[j + k];
-          const Vertex* p = id < a.hot_n ? a.x_hot + id : a.x_old + (id - a.hot_n);
-          val[k] = Prog::gather(__ldg(p));
+          const bool hot = id < a.hot_n;
+          const Vertex* p = hot ? a.x_hot + id : a.x_old + (id - a.hot_n);
+          val[k] = Prog::gather(gather_load(p, hot));
         }
 
       // ---- serial walk: edges [j, j_next) merged with vertex-end markers [i, i_next) ----

@@ -79,6 +79,7 @@ struct luxb_graph {
   void* peer_val[2][LUXB_MAX_PARTS]{};  // imported replicas of the peers (P2P exchange)
   void* peer_hot[LUXB_MAX_PARTS]{};
   uint32_t* d_sync = nullptr;
+  uint64_t ag_chunk = 0, hot_chunk = 0;  // equal chunk sizes (elements) of the balanced all-gather
 
   // optional per-launch timing of the dominant kernel
   bool kernel_timing = false;
