@@ -43,6 +43,7 @@ def parse_args():
                     help="auto = fused P2P stores up to 4 GPUs (measured best), NCCL at 8")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-ref-gpu", action="store_true")
     return ap.parse_args()
 
 
@@ -293,6 +294,32 @@ def main():
         except Exception:  # noqa: BLE001
             pass
 
+    # ---- the reference's OWN CUDA kernels on the same box (oracle/_ref/libref_pagerank.so: pagerank_gpu.cu compiled
+    # unmodified behind a Legion shim, zero-copy regions emulated with mapped pinned memory).  Its init does a host
+    # std::sort of all edges (pagerank_gpu.cu:229-242), minutes at RMAT-27, so both engines are timed on RMAT-24. ----
+    ref_gpu = None
+    if rank == 0 and world == 1 and not args.no_ref_gpu:
+        try:
+            from oracle import refrun as R
+            if R.available("pagerank"):
+                sc = min(scale, 24)
+                nv2, ne2 = 1 << sc, args.edge_factor << sc
+                with L.LuxGraph.from_rmat(sc, nv2, ne2, SEED, device=local) as g2:
+                    re2, src2 = g2.local_csc()
+                    g2.init()
+                    g2.iterate(3)
+                    a0 = g2.stats()
+                    g2.iterate(ITERS_PER_STEP)
+                    a1 = g2.stats()
+                    ours_ms = 1e3 * (a1["loop_seconds"] - a0["loop_seconds"]) / ITERS_PER_STEP
+                _, ref_ms = R.pagerank(re2, src2, ITERS_PER_STEP)
+                ref_ms /= ITERS_PER_STEP
+                ref_gpu = {"workload": "pagerank_pull_rmat%d" % sc, "reference_MTEPS": ne2 / ref_ms / 1e3,
+                           "ours_MTEPS_same_graph": ne2 / ours_ms / 1e3, "reference_ms_per_iter": ref_ms,
+                           "ours_ms_per_iter": ours_ms, "how": "reference task bodies + kernels replayed (oracle/ref_replay), 1 partition"}
+        except Exception as e:  # noqa: BLE001
+            ref_gpu = {"unavailable": repr(e)[:200]}
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         row_end, src = g.local_csc()
@@ -307,7 +334,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": 1e3 * dev_s_max / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "e2e": e2e, "gpu_launches": total_launches, "roofline": roofline, "cpu_baseline": cpu_base,
-                "clocks": clocks, "wall_ms_per_step": 1e3 * wall_s_max / args.steps, "build_seconds": t_build,
+                "reference_gpu_replay": ref_gpu, "clocks": clocks, "wall_ms_per_step": 1e3 * wall_s_max / args.steps, "build_seconds": t_build,
                 "exchange": args.exchange if world > 1 else "none",
                 "roofline_whole_step": {"algorithmic_GBps_per_gpu": (8 * ne + 16 * nv) * ITERS_PER_STEP * args.steps
                                         / world / dev_s_max / 1e9, "frac": (8 * ne + 16 * nv) * ITERS_PER_STEP

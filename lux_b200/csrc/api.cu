@@ -209,8 +209,8 @@ static int finish_layout(luxb_graph* g) {
   LUXB_TRY(dmalloc(&g->d_carry_flag, (uint64_t)g->n_tiles + 1));
   LUXB_TRY(dmalloc((uint64_t**)&g->d_block_agg, (uint64_t)g->n_fix_blocks + 1));
   LUXB_TRY(dmalloc(&g->d_block_flag, (uint64_t)g->n_fix_blocks + 1));
-  LUXB_TRY(dmalloc(&g->d_counters, 4));
-  LUXB_CUDA(cudaMemsetAsync(g->d_counters, 0, 4 * sizeof(unsigned long long), g->stream));
+  LUXB_TRY(dmalloc(&g->d_counters, 8));
+  LUXB_CUDA(cudaMemsetAsync(g->d_counters, 0, 8 * sizeof(unsigned long long), g->stream));
   LUXB_CUDA(cudaStreamSynchronize(g->stream));
   return 0;
 }
@@ -789,6 +789,8 @@ int luxb_init(luxb_graph* g) {
       LUXB_TRY(dmalloc((uint32_t**)&g->d_val[0], g->nv));
       LUXB_TRY(dmalloc(&g->d_cur, g->n_part));
       LUXB_TRY(build_push_csr(g));
+      g->big_capacity = (uint32_t)std::min<uint64_t>(g->e_part / kPushBigDegree + 1024, 0x7FFFFFFFull);
+      LUXB_TRY(dmalloc((PushArgs::BigSeg**)&g->d_big_list, g->big_capacity));
       LUXB_TRY(dmalloc(&g->d_fq_all, g->fq_total));
       LUXB_TRY(dmalloc(&g->d_fq_new, g->slot_bytes[g->cfg.rank]));
       LUXB_TRY(dmalloc(&g->d_fq_tmp, g->slot_bytes[g->cfg.rank]));
@@ -1070,10 +1072,15 @@ static int label_iteration(luxb_graph* g) {
     a.new_queue = reinterpret_cast<uint32_t*>(new_slot + 8);
     a.max_nodes = max_nodes;
     a.edges_scanned = g->d_counters;
+    a.big_list = reinterpret_cast<PushArgs::BigSeg*>(g->d_big_list);
+    a.big_count = reinterpret_cast<uint32_t*>(g->d_counters + 3);
+    a.big_capacity = g->big_capacity;
     if (blocks) {
+      LUXB_CUDA(cudaMemsetAsync(a.big_count, 0, 4, g->stream));
       push_relax_kernel<Prog><<<(unsigned)blocks, kPushThreads, 0, g->stream>>>(a);
+      push_big_kernel<Prog><<<g->num_sms * 4, kPushThreads, 0, g->stream>>>(a);
       LUXB_CUDA(cudaGetLastError());
-      g->stats.kernel_launches++;
+      g->stats.kernel_launches += 2;
     }
   }
 
@@ -1414,7 +1421,7 @@ void luxb_close(luxb_graph* g) {
   void* ptrs[] = {g->d_row_end, g->d_row_end32, g->d_src, g->d_weight, g->d_tile_v, g->d_head, g->d_tail, g->d_deg, g->d_val[0], g->d_val[1],
                   g->d_cur, g->d_out_end, g->d_out_dst, g->d_fq_all, g->d_fq_new, g->d_fq_tmp, g->d_hdr_all, g->d_counters,
                   g->d_chunk_first, g->d_chunk_vtx, g->d_partial, g->d_sync, g->d_hot_order, g->d_src_gather,
-                  g->d_carry, g->d_carry_flag, g->d_block_agg, g->d_block_flag, g->d_hot};
+                  g->d_carry, g->d_carry_flag, g->d_block_agg, g->d_block_flag, g->d_hot, g->d_big_list};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (g->h_hdr) cudaFreeHost(g->h_hdr);

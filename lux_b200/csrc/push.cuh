@@ -42,9 +42,48 @@ struct PushArgs {
   uint32_t* new_queue;
   uint32_t max_nodes;
   unsigned long long* edges_scanned;
+  // sources with more than kPushBigDegree local out-edges are not relaxed inline: their edge list is cut into
+  // kPushSegment-edge segments appended here and swept by push_big_kernel (one CTA per segment) — a hub with 10^6
+  // out-edges would otherwise serialise on one CTA (the reference's kernel has exactly that problem)
+  struct BigSeg { uint64_t begin; uint32_t len; uint32_t val; };
+  BigSeg* big_list;
+  uint32_t* big_count;
+  uint32_t big_capacity;
 };
 
+constexpr uint32_t kPushBigDegree = 2048;
+constexpr uint32_t kPushSegment = 4096;
+
 constexpr int kPushThreads = 256;
+
+// one relaxation: atomics on this GPU's own slice only; returns true iff this thread must enqueue dst
+template <class Prog>
+__device__ __forceinline__ bool relax_edge(const PushArgs& a, uint32_t dstv, uint32_t cand) {
+  uint32_t* addr = a.cur + (dstv - a.row_left);
+  uint32_t seen = *reinterpret_cast<volatile uint32_t*>(addr);
+  if (Prog::better(cand, seen)) {
+    uint32_t prev = Prog::atomic_relax(addr, cand);
+    // exactly-once enqueue: the thread that moves the label off its iteration-start value owns the append
+    // (process_edge_sparse, components_gpu.cu:75-79)
+    if (a.new_sparse && Prog::better(cand, prev) && prev == a.lab[dstv]) return true;
+  }
+  return false;
+}
+// warp-aggregated append to the new frontier queue: ONE atomic per warp
+__device__ __forceinline__ void enqueue_warp(const PushArgs& a, bool enq, uint32_t dstv, int lane) {
+  if (!a.new_sparse) return;
+  unsigned m = __ballot_sync(0xffffffffu, enq);
+  if (m) {
+    int leader = __ffs(m) - 1;
+    uint32_t pos = 0;
+    if (lane == leader) pos = atomicAdd(a.new_count, (uint32_t)__popc(m));
+    pos = __shfl_sync(0xffffffffu, pos, leader);
+    if (enq) {
+      pos += __popc(m & ((1u << lane) - 1));
+      if (pos < a.max_nodes) a.new_queue[pos] = dstv;
+    }
+  }
+}
 
 // Each CTA takes kPushThreads frontier entries, scans their out-degrees (warp shuffles + smem), then all
 // threads sweep the concatenated out-edge list; the owning source of an edge is found by binary search in the
@@ -91,6 +130,19 @@ __global__ void __launch_bounds__(kPushThreads) push_relax_kernel(const __grid_c
       begin = u == 0 ? 0 : a.out_end[u - 1];
       deg = e1 - begin;
       val = Prog::gather(a.lab[u]);
+      if (deg > kPushBigDegree) {
+        uint32_t n_seg = (uint32_t)((deg + kPushSegment - 1) / kPushSegment);
+        uint32_t pos = atomicAdd(a.big_count, n_seg);
+        for (uint32_t q = 0; q < n_seg && pos + q < a.big_capacity; ++q) {
+          PushArgs::BigSeg sg;
+          sg.begin = begin + (uint64_t)q * kPushSegment;
+          uint64_t rem = deg - (uint64_t)q * kPushSegment;
+          sg.len = (uint32_t)(rem < kPushSegment ? rem : kPushSegment);
+          sg.val = val;
+          a.big_list[pos + q] = sg;
+        }
+        deg = 0;
+      }
     }
   }
   // a single source with >= 2^32 local out-edges is impossible (e_part per CTA chunk is summed in u64 below)
@@ -124,28 +176,30 @@ __global__ void __launch_bounds__(kPushThreads) push_relax_kernel(const __grid_c
         if (s_scan[mid] <= e) lo = mid; else hi = mid;
       }
       dstv = a.out_dst[s_begin[lo] + (e - s_scan[lo])];
-      uint32_t cand = s_val[lo];
-      uint32_t* addr = a.cur + (dstv - a.row_left);
-      uint32_t seen = *reinterpret_cast<volatile uint32_t*>(addr);
-      if (Prog::better(cand, seen)) {
-        uint32_t prev = Prog::atomic_relax(addr, cand);
-        // exactly-once enqueue: the thread that moves the label off its iteration-start value owns the append
-        // (process_edge_sparse, components_gpu.cu:75-79)
-        if (a.new_sparse && Prog::better(cand, prev) && prev == a.lab[dstv]) enq = true;
-      }
+      enq = relax_edge<Prog>(a, dstv, s_val[lo]);
     }
-    if (a.new_sparse) {
-      unsigned m = __ballot_sync(0xffffffffu, enq);
-      if (m) {
-        int leader = __ffs(m) - 1;
-        uint32_t pos = 0;
-        if (lane == leader) pos = atomicAdd(a.new_count, (uint32_t)__popc(m));
-        pos = __shfl_sync(0xffffffffu, pos, leader);
-        if (enq) {
-          pos += __popc(m & ((1u << lane) - 1));
-          if (pos < a.max_nodes) a.new_queue[pos] = dstv;
-        }
+    enqueue_warp(a, enq, dstv, lane);
+  }
+}
+
+// hubs: one CTA per kPushSegment-edge segment of a big source's out-edge list (persistent grid-stride)
+template <class Prog>
+__global__ void __launch_bounds__(kPushThreads) push_big_kernel(const __grid_constant__ PushArgs a) {
+  const int lane = threadIdx.x & 31;
+  uint32_t n = *a.big_count;
+  if (n > a.big_capacity) n = a.big_capacity;
+  for (uint32_t sidx = blockIdx.x; sidx < n; sidx += gridDim.x) {
+    const PushArgs::BigSeg sg = a.big_list[sidx];
+    if (threadIdx.x == 0) atomicAdd(a.edges_scanned, (unsigned long long)sg.len);
+    for (uint32_t base = 0; base < sg.len; base += kPushThreads) {
+      uint32_t e = base + threadIdx.x;
+      bool enq = false;
+      uint32_t dstv = 0;
+      if (e < sg.len) {
+        dstv = a.out_dst[sg.begin + e];
+        enq = relax_edge<Prog>(a, dstv, sg.val);
       }
+      enqueue_warp(a, enq, dstv, lane);
     }
   }
 }

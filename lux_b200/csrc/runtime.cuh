@@ -60,6 +60,8 @@ struct luxb_graph {
   uint32_t* d_cur = nullptr;       // [n_part] working labels of this partition
   uint64_t* d_out_end = nullptr;   // [nv] CSR-by-source end offsets over this partition's edges
   uint32_t* d_out_dst = nullptr;   // [e_part]
+  void* d_big_list = nullptr;      // segments of hub sources' out-edge lists (push_big_kernel)
+  uint32_t big_capacity = 0;
   unsigned char* d_fq_all = nullptr;  // every partition's frontier slot as exchanged
   unsigned char* d_fq_new = nullptr;  // this partition's slot under construction
   unsigned char* d_fq_tmp = nullptr;
