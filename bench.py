@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--scale", type=int, default=27, help="RMAT scale (27 = BASELINE config; smaller only for debugging)")
     ap.add_argument("--edge-factor", type=int, default=16)
     ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "p2p", "p2p_fused"],
-                    help="auto = fused P2P stores up to 4 GPUs (measured best), NCCL at 8")
+                    help="auto = fused P2P stores up to 4 GPUs, balanced all-gather (re-chunk + ncclAllGather) beyond (measured best)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
@@ -201,7 +201,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if args.exchange == "auto":
-        args.exchange = "p2p_fused" if world <= 4 else "nccl"
+        args.exchange = "p2p_fused" if world <= 4 else "p2p"
     exchange = {"p2p": L.EXCHANGE_P2P, "p2p_fused": L.EXCHANGE_P2P_FUSED, "nccl": L.EXCHANGE_NCCL}[args.exchange]
     t_build0 = time.perf_counter()
     g = L.LuxGraph.from_rmat(scale, nv, ne, SEED, rank=rank, nranks=world, device=local, exchange=exchange)
