@@ -125,25 +125,26 @@ def cpu_baseline_pagerank(row_end, src, deg, x_old, steps, target_s=6.0):
         O.pagerank_iter(row_end, src, deg, x_old, 0, v_hi, out=out)
         return time.perf_counter() - t0
 
-    # probe on a small prefix: pick the thread count (all logical CPUs or half of them — SMT siblings often hurt a
-    # latency-bound gather) and the sample size
+    # size the sample on a small prefix, then pick the thread count (all logical CPUs or half of them — SMT siblings
+    # often hurt a latency-bound gather) ON THE SAMPLE ITSELF: prefix ranges are hub-heavy and mislead
     probe_hi = int(np.searchsorted(row_end, ne // 32, side="left"))
     probe_hi = min(max(probe_hi, 0), nv - 1)
     e_probe = int(row_end[probe_hi])
     ncpu = os.cpu_count() or 1
-    best_t, best_n = None, ncpu
-    for nthr in sorted({ncpu, max(1, ncpu // 2)}, reverse=True):
-        O.set_num_threads(nthr)
-        run(probe_hi)
-        t = min(run(probe_hi), run(probe_hi))
-        if best_t is None or t < best_t:
-            best_t, best_n = t, nthr
-    O.set_num_threads(best_n)
-    rate = e_probe / max(best_t, 1e-9)
+    O.set_num_threads(ncpu)
+    run(probe_hi)
+    rate = e_probe / max(min(run(probe_hi), run(probe_hi)), 1e-9)
     want_edges = min(ne, int(rate * target_s))
     v_hi = nv - 1 if want_edges >= ne else int(np.searchsorted(row_end, want_edges, side="left"))
     v_hi = min(max(v_hi, probe_hi), nv - 1)
     edges = int(row_end[v_hi])
+    best_t, best_n = None, ncpu
+    for nthr in sorted({ncpu, max(1, ncpu // 2)}, reverse=True):
+        O.set_num_threads(nthr)
+        t = run(v_hi)
+        if best_t is None or t < best_t:
+            best_t, best_n = t, nthr
+    O.set_num_threads(best_n)
     times = [run(v_hi) for _ in range(max(steps, 1))]
     best = float(np.median(times))
     desc = "1 PageRank iteration over destination vertices [0,%d] = %d of %d edges, median of %d runs" % (
