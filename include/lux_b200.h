@@ -79,6 +79,9 @@ typedef struct {
   luxb_vid start_vtx;  /* SSSP -start (sssp.cc) */
   luxb_exchange exchange;
   int verbose;         /* -verbose: per-iteration line like components_gpu.cu:516-518 */
+  int zero_copy_edges; /* 1: keep the edge arrays (source ids, weights) in mapped pinned HOST memory and stream them
+                          over PCIe every iteration — the analogue of Legion's -ll:zsize zero-copy memory for
+                          graphs larger than HBM (lux_mapper.cc:146-165); vertex arrays stay in HBM */
 } luxb_config;
 
 typedef struct luxb_graph luxb_graph; /* opaque; owns all device memory (Graph + GraphPiece, core/graph.h:54-98) */

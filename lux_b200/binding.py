@@ -28,7 +28,7 @@ class _Csc(C.Structure):
 
 class _Config(C.Structure):
     _fields_ = [("app", C.c_int), ("rank", C.c_int), ("nranks", C.c_int), ("device", C.c_int),
-                ("start_vtx", C.c_uint32), ("exchange", C.c_int), ("verbose", C.c_int)]
+                ("start_vtx", C.c_uint32), ("exchange", C.c_int), ("verbose", C.c_int), ("zero_copy_edges", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -109,18 +109,18 @@ class LuxGraph:
 
     # ---- constructors -------------------------------------------------------------------------------------
     @staticmethod
-    def _cfg(app, rank, nranks, device, start, exchange, verbose):
-        return _Config(app, rank, nranks, device, start, exchange, 1 if verbose else 0)
+    def _cfg(app, rank, nranks, device, start, exchange, verbose, zero_copy=False):
+        return _Config(app, rank, nranks, device, start, exchange, 1 if verbose else 0, 1 if zero_copy else 0)
 
     @classmethod
     def from_csc(cls, row_end, src, weight=None, app=APP_PAGERANK, rank=0, nranks=1, device=0, start=0,
-                 exchange=EXCHANGE_NCCL, verbose=False):
+                 exchange=EXCHANGE_NCCL, verbose=False, zero_copy=False):
         row_end = np.ascontiguousarray(row_end, np.uint64)
         src = np.ascontiguousarray(src, np.uint32)
         if weight is not None:
             weight = np.ascontiguousarray(weight, np.int32)
         csc = _Csc(len(row_end), len(src), _p(row_end), _p(src) if len(src) else None, _p(weight))
-        cfg = cls._cfg(app, rank, nranks, device, start, exchange, verbose)
+        cfg = cls._cfg(app, rank, nranks, device, start, exchange, verbose, zero_copy)
         h = C.c_void_p()
         _chk(load_library().luxb_open_csc(C.byref(csc), C.byref(cfg), C.byref(h)), "luxb_open_csc")
         return cls(h, app, rank, nranks)
@@ -135,8 +135,8 @@ class LuxGraph:
 
     @classmethod
     def from_rmat(cls, scale, nv, ne, seed, app=APP_PAGERANK, rank=0, nranks=1, device=0, start=0,
-                  exchange=EXCHANGE_NCCL, verbose=False):
-        cfg = cls._cfg(app, rank, nranks, device, start, exchange, verbose)
+                  exchange=EXCHANGE_NCCL, verbose=False, zero_copy=False):
+        cfg = cls._cfg(app, rank, nranks, device, start, exchange, verbose, zero_copy)
         h = C.c_void_p()
         _chk(load_library().luxb_open_rmat(C.c_int(scale), C.c_uint32(nv), C.c_uint64(ne), C.c_uint64(seed),
                                            C.byref(cfg), C.byref(h)), "luxb_open_rmat")

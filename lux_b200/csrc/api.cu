@@ -106,6 +106,18 @@ static int dmalloc(T** p, uint64_t count) {
   return 0;
 }
 
+// edge arrays: HBM, or mapped pinned host memory when cfg.zero_copy_edges (TMA bulk copies and plain loads read it
+// over PCIe through the same unified addresses)
+template <class T>
+static int edge_alloc(luxb_graph* g, T** p, uint64_t count) {
+  if (!g->cfg.zero_copy_edges) return dmalloc(p, count);
+  void* q = nullptr;
+  LUXB_CUDA(cudaHostAlloc(&q, std::max<uint64_t>(count, 1) * sizeof(T) + 256, cudaHostAllocMapped | cudaHostAllocPortable));
+  g->host_allocs.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return 0;
+}
+
 // ---- the reference partitioner on the host (pull_model.inl:108-131); same cut rule as partition_kernel -------
 static int host_partition(uint32_t nv, uint64_t ne, const uint64_t* row_end, int P, uint32_t* rl, uint32_t* np,
                           uint64_t* cl) {
@@ -228,7 +240,7 @@ static int validate_row_end(uint32_t nv, uint64_t ne, const uint64_t* row_end) {
 static int upload_slice(luxb_graph* g, const uint64_t* row_end_slice_abs, const uint32_t* src_slice,
                         const int32_t* weight_slice) {
   LUXB_TRY(dmalloc(&g->d_row_end, (uint64_t)g->n_part + 4));
-  LUXB_TRY(dmalloc(&g->d_src, g->e_part + 8));
+  LUXB_TRY(edge_alloc(g, &g->d_src, g->e_part + 8));
   uint64_t* d_tmp = nullptr;
   LUXB_TRY(dmalloc(&d_tmp, (uint64_t)g->n_part + 1));
   if (g->n_part)
@@ -239,7 +251,7 @@ static int upload_slice(luxb_graph* g, const uint64_t* row_end_slice_abs, const 
   LUXB_CUDA(cudaMemsetAsync(g->d_src, 0, (g->e_part + 8) * 4, g->stream));
   if (g->e_part) LUXB_CUDA(cudaMemcpyAsync(g->d_src, src_slice, g->e_part * 4, cudaMemcpyHostToDevice, g->stream));
   if (g->weighted) {
-    LUXB_TRY(dmalloc(&g->d_weight, g->e_part + 8));
+    LUXB_TRY(edge_alloc(g, &g->d_weight, g->e_part + 8));
     LUXB_CUDA(cudaMemsetAsync(g->d_weight, 0, (g->e_part + 8) * 4, g->stream));
     if (g->e_part) LUXB_CUDA(cudaMemcpyAsync(g->d_weight, weight_slice, g->e_part * 4, cudaMemcpyHostToDevice, g->stream));
   }
@@ -402,10 +414,10 @@ static int open_generated(const GenSpec& spec, const luxb_config* cfg, luxb_grap
   GEN_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys, (long long)g->e_part, 0, 32 + pbits, g->stream));
   GEN_CUDA(cudaMalloc(&d_tmp, tmp_bytes + 256));
   GEN_CUDA(cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, keys, (long long)g->e_part, 0, 32 + pbits, g->stream));
-  if ((rc = dmalloc(&g->d_src, g->e_part + 8))) return fail(rc);
+  if ((rc = edge_alloc(g, &g->d_src, g->e_part + 8))) return fail(rc);
   GEN_CUDA(cudaMemsetAsync(g->d_src, 0, (g->e_part + 8) * 4, g->stream));
   if (g->weighted) {
-    if ((rc = dmalloc(&g->d_weight, g->e_part + 8))) return fail(rc);
+    if ((rc = edge_alloc(g, &g->d_weight, g->e_part + 8))) return fail(rc);
     GEN_CUDA(cudaMemsetAsync(g->d_weight, 0, (g->e_part + 8) * 4, g->stream));
   }
   keys_to_src_kernel<<<gen_grid, 256, 0, g->stream>>>(keys.Current(), g->e_part, g->d_src, g->d_weight, spec.seed, g->row_left);
@@ -711,7 +723,7 @@ static int build_hot_layout(luxb_graph* g) {
   LUXB_TRY(dmalloc(&d_map, g->nv));
   gather_map_init_kernel<<<grid, 256, 0, g->stream>>>(d_map, g->nv, H);
   gather_map_hot_kernel<<<grid, 256, 0, g->stream>>>(d_map, g->d_hot_order, H);
-  LUXB_TRY(dmalloc(&g->d_src_gather, g->e_part + 8));
+  LUXB_TRY(edge_alloc(g, &g->d_src_gather, g->e_part + 8));
   LUXB_CUDA(cudaMemsetAsync(g->d_src_gather, 0, (g->e_part + 8) * 4, g->stream));
   remap_src_kernel<<<grid, 256, 0, g->stream>>>(g->d_src, g->e_part, d_map, g->d_src_gather);
   LUXB_CUDA(cudaGetLastError());
@@ -1422,8 +1434,11 @@ void luxb_close(luxb_graph* g) {
                   g->d_cur, g->d_out_end, g->d_out_dst, g->d_fq_all, g->d_fq_new, g->d_fq_tmp, g->d_hdr_all, g->d_counters,
                   g->d_chunk_first, g->d_chunk_vtx, g->d_partial, g->d_sync, g->d_hot_order, g->d_src_gather,
                   g->d_carry, g->d_carry_flag, g->d_block_agg, g->d_block_flag, g->d_hot, g->d_big_list};
-  for (void* p : ptrs)
-    if (p) cudaFree(p);
+  for (void* p : ptrs) {
+    if (!p) continue;
+    if (std::find(g->host_allocs.begin(), g->host_allocs.end(), p) != g->host_allocs.end()) cudaFreeHost(p);
+    else cudaFree(p);
+  }
   if (g->h_hdr) cudaFreeHost(g->h_hdr);
   if (g->h_scratch) cudaFreeHost(g->h_scratch);
   for (cudaEvent_t e : g->kt_events) cudaEventDestroy(e);

@@ -349,12 +349,14 @@ __global__ void __launch_bounds__(kFixBlock) pull_fixup_scan_kernel(const __grid
   }
 }
 
-// exclusive scan of the block aggregates, in place, by one CTA (serial chunks + one smem pass)
+// exclusive scan of the block aggregates, in place, by one CTA: serial chunk per thread, then a segmented scan of the
+// 1024 chunk aggregates with warp shuffles (two levels), then the chunk is rewritten as exclusive prefixes
 template <class Prog>
 __global__ void __launch_bounds__(1024) pull_fixup_blocks_kernel(const __grid_constant__ PullArgs<Prog> a, uint32_t n_blocks) {
   using Wide = typename Prog::Wide;
-  __shared__ Wide s_v[1024];
-  __shared__ uint32_t s_f[1024];
+  __shared__ Wide s_v[32];
+  __shared__ uint32_t s_f[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t per = (n_blocks + 1023) / 1024;
   const uint32_t b0 = threadIdx.x * per < n_blocks ? threadIdx.x * per : n_blocks;
   const uint32_t b1 = b0 + per < n_blocks ? b0 + per : n_blocks;
@@ -366,17 +368,29 @@ __global__ void __launch_bounds__(1024) pull_fixup_blocks_kernel(const __grid_co
     seg_combine<Prog>(f2, v2, cf, cv);
     cf = f2; cv = v2;
   }
-  s_v[threadIdx.x] = cv;
-  s_f[threadIdx.x] = cf;
-  __syncthreads();
-  Wide pv = Prog::widen(Prog::identity());
-  uint32_t pf = 0;
-  for (uint32_t k = 0; k < threadIdx.x; ++k) {
-    uint32_t f2 = s_f[k];
-    Wide v2 = s_v[k];
-    seg_combine<Prog>(f2, v2, pf, pv);
-    pf = f2; pv = v2;
+  // inclusive segmented scan of (cf, cv) over the 1024 threads
+  Wide sv = cv;
+  uint32_t sf = cf;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    Wide pv = __shfl_up_sync(0xffffffffu, sv, off);
+    uint32_t pf = __shfl_up_sync(0xffffffffu, sf, off);
+    if (lane >= off) seg_combine<Prog>(sf, sv, pf, pv);
   }
+  if (lane == 31) { s_v[warp] = sv; s_f[warp] = sf; }
+  __syncthreads();
+  Wide wv = Prog::widen(Prog::identity());
+  uint32_t wf = 0;
+  for (int w = 0; w < warp; ++w) {
+    uint32_t f2 = s_f[w];
+    Wide v2 = s_v[w];
+    seg_combine<Prog>(f2, v2, wf, wv);
+    wf = f2; wv = v2;
+  }
+  Wide pv = __shfl_up_sync(0xffffffffu, sv, 1);  // exclusive prefix of this thread = agg(prev warps) (+) incl(lane-1)
+  uint32_t pf = __shfl_up_sync(0xffffffffu, sf, 1);
+  if (lane == 0) { pv = Prog::widen(Prog::identity()); pf = 0; }
+  seg_combine<Prog>(pf, pv, wf, wv);
   for (uint32_t b = b0; b < b1; ++b) {  // rewrite aggregates as exclusive prefixes
     uint32_t f2 = a.block_flag[b];
     Wide v2 = a.block_agg[b];

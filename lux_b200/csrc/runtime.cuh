@@ -88,6 +88,8 @@ struct luxb_graph {
   std::vector<cudaEvent_t> kt_events;  // pairs
   size_t kt_used = 0;
 
+  std::vector<void*> host_allocs;  // edge arrays living in mapped pinned host memory (cfg.zero_copy_edges)
+
   // stats / trace
   luxb_stats_t stats{};
   std::vector<uint64_t> trace_active;
