@@ -209,7 +209,8 @@ def main():
     g.comm_init_torch()
     g.init()
     if world > 1 and exchange != L.EXCHANGE_NCCL:
-        g.p2p_connect_torch()
+        if not g.p2p_connect_torch():  # CUDA IPC unavailable on some rank: every rank degrades to the NCCL exchange
+            args.exchange = "nccl (p2p import failed)"
     t_build = time.perf_counter() - t_build0
     view = g.device_view()
     n_part = (view.row_right - view.row_left + 1) & 0xFFFFFFFF

@@ -118,6 +118,9 @@ int luxb_comm_init(luxb_graph* g, const char id[LUXB_UNIQUE_ID_BYTES]); /* colle
  * blobs (any transport) and hands the full table back. */
 int luxb_p2p_export(luxb_graph* g, void* blob, size_t* blob_bytes);
 int luxb_p2p_import(luxb_graph* g, const void* all_blobs, size_t blob_bytes_each);
+/* Forget imported peer mappings: the P2P exchanges silently degrade to the NCCL exchange.  Call on EVERY rank when the
+ * import failed on any of them (all ranks must use the same exchange). */
+int luxb_p2p_disable(luxb_graph* g);
 
 /* ---- Pull/PushInitTask (+PullScanTask): app state ------------------------------------------------------- */
 /* = pull_scan_task_impl (pull_model.inl:322-345) + pull_init_task_impl (pagerank_gpu.cu:182-281,

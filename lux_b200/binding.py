@@ -179,19 +179,37 @@ class LuxGraph:
         self.comm_init(obj[0])
 
     def p2p_connect_torch(self):
-        """Exchange cudaIpc handles of the replicas so kernels can store into peer HBM (exchange=P2P)."""
+        """Exchange cudaIpc handles of the replicas so kernels / copy engines can write into peer HBM (exchange=P2P*).
+        Collective and all-or-nothing: if the import fails on any rank, every rank falls back to the NCCL exchange.
+        Returns True when the peer mappings are in place."""
         if self.nranks == 1:
-            return
+            return True
+        import torch
         import torch.distributed as dist
         L = load_library()
-        n = C.c_size_t(0)
-        _chk(L.luxb_p2p_export(self._h, None, C.byref(n)), "luxb_p2p_export")
-        buf = C.create_string_buffer(n.value)
-        _chk(L.luxb_p2p_export(self._h, buf, C.byref(n)), "luxb_p2p_export")
+        ok = 1
+        try:
+            n = C.c_size_t(0)
+            _chk(L.luxb_p2p_export(self._h, None, C.byref(n)), "luxb_p2p_export")
+            buf = C.create_string_buffer(n.value)
+            _chk(L.luxb_p2p_export(self._h, buf, C.byref(n)), "luxb_p2p_export")
+            blob = buf.raw
+        except LuxError:
+            ok, blob, n = 0, b"", C.c_size_t(0)
         blobs = [None] * self.nranks
-        dist.all_gather_object(blobs, buf.raw)
-        allb = b"".join(blobs)
-        _chk(L.luxb_p2p_import(self._h, allb, C.c_size_t(n.value)), "luxb_p2p_import")
+        dist.all_gather_object(blobs, blob)
+        if ok and all(len(b) == n.value for b in blobs):
+            if L.luxb_p2p_import(self._h, b"".join(blobs), C.c_size_t(n.value)) < 0:
+                ok = 0
+        else:
+            ok = 0
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag) == 0:
+            L.luxb_p2p_disable(self._h)
+            return False
+        return True
 
     # ---- phases -------------------------------------------------------------------------------------------
     def init(self):

@@ -82,7 +82,7 @@ void set_error(const char* fmt, ...) {
 // Shared memory is kept small on purpose: what the ring does not take stays L1, and the gather rate follows L1 size.
 #define LUXB_PULL_SHAPES(X) \
   X(0, 7, 8, 2) X(1, 9, 8, 2) X(2, 11, 8, 2) X(3, 13, 8, 2) X(4, 15, 8, 2) X(5, 7, 16, 2) X(6, 9, 16, 2) X(7, 11, 16, 2) \
-  X(8, 11, 8, 3) X(9, 5, 16, 2)
+  X(8, 11, 8, 3) X(9, 5, 16, 2) X(10, 7, 12, 2) X(11, 7, 24, 2)
 #define LUXB_DECL_SHAPE(id, ipt, warps, stages) using PullShape##id = PullShape<ipt, warps, stages>;
 LUXB_PULL_SHAPES(LUXB_DECL_SHAPE)
 #define LUXB_TILE_OF(id, ipt, warps, stages) PullShape##id::kTile,
@@ -542,6 +542,12 @@ int luxb_p2p_import(luxb_graph* g, const void* all_blobs, size_t blob_bytes_each
     }
   }
   g->p2p_ready = true;
+  return 0;
+}
+
+int luxb_p2p_disable(luxb_graph* g) {
+  LUXB_ARG(g != nullptr, "graph is NULL");
+  g->p2p_ready = false;
   return 0;
 }
 
