@@ -438,7 +438,7 @@ static int open_generated(const GenSpec& spec, const luxb_config* cfg, luxb_grap
 int luxb_open_rmat(int scale, luxb_vid nv, luxb_eid ne, uint64_t seed, const luxb_config* cfg, luxb_graph** out) {
   LUXB_TRY(check_config(cfg));
   LUXB_ARG(scale >= 1 && scale <= 31, "scale out of range");
-  LUXB_ARG(nv >= 1 && (uint64_t)nv <= (1ull << scale), "nv must be in [1, 2^scale]");
+  LUXB_ARG(nv >= 1 && (uint64_t)nv <= (1ull << scale) && nv < 0x7FFFFFFFu, "nv must be in [1, min(2^scale, 2^31 - 2)]");
   LUXB_ARG(cfg->app != LUXB_COLFILTER, "use luxb_open_bipartite for col_filter");
   GenSpec s{};
   s.kind = 0; s.scale = scale; s.nv = nv; s.ne = ne; s.seed = seed;
@@ -851,8 +851,12 @@ static int p2p_barrier(luxb_graph* g) {
 extern "C++" {
 template <class Prog, class Shape>
 static int launch_pull_shape(luxb_graph* g, const PullArgs<Prog>& a) {
-  static int attr_ctas = -1;
-  static int occ = 0;
+  static int attr_ctas_dev[64];  // function attributes are per device: remember what each device was given
+  static int occ_dev[64];
+  static bool attr_init = false;
+  if (!attr_init) { for (int d = 0; d < 64; ++d) { attr_ctas_dev[d] = -1; occ_dev[d] = 0; } attr_init = true; }
+  int& attr_ctas = attr_ctas_dev[g->cfg.device & 63];
+  int& occ = occ_dev[g->cfg.device & 63];
   auto kern = pull_tile_kernel<Prog, Shape>;
   int want = kDefaultPullCtas;
   if (const char* env = getenv("LUXB_PULL_CTAS")) want = atoi(env);
