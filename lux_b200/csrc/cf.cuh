@@ -14,6 +14,10 @@ namespace luxb {
 
 constexpr int kCfK = LUXB_CF_K;
 constexpr int kCfChunk = 256;
+#ifndef LUXB_CF_UNROLL
+#define LUXB_CF_UNROLL 4
+#endif
+constexpr int kCfUnroll = LUXB_CF_UNROLL;  // 32 edges per load round must be a multiple of 4 * kCfUnroll
 constexpr float kCfLambda = 0.001f;       // LAMBDA, col_filter/app.h:26
 constexpr float kCfGamma = 0.00000035f;   // GAMMA,  col_filter/app.h:27
 
@@ -64,25 +68,36 @@ __global__ void __launch_bounds__(256) cf_chunk_kernel(const __grid_constant__ C
       int32_t w = 0;
       if (me < e) { s = __ldg(a.src + me); w = __ldg(a.weight + me); }
       uint32_t n = e - base < 32 ? (uint32_t)(e - base) : 32u;
-      for (uint32_t q = 0; q < n; q += 4) {
-        uint32_t idx = q + grp;
-        uint32_t su = __shfl_sync(0xffffffffu, s, idx & 31);
-        int32_t wu = __shfl_sync(0xffffffffu, w, idx & 31);
-        bool valid = idx < n;
-        float4 xu = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid && holder) xu = __ldg(reinterpret_cast<const float4*>(a.x_old + (size_t)su * kCfK) + sub);
-        float dot = xu.x * xv.x;
-        dot = __fmaf_rn(xu.y, xv.y, dot);
-        dot = __fmaf_rn(xu.z, xv.z, dot);
-        dot = __fmaf_rn(xu.w, xv.w, dot);
-        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-        dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-        float err = valid ? (float)wu - dot : 0.f;
-        acc.x = __fmaf_rn(err, xu.x, acc.x);
-        acc.y = __fmaf_rn(err, xu.y, acc.y);
-        acc.z = __fmaf_rn(err, xu.z, acc.z);
-        acc.w = __fmaf_rn(err, xu.w, acc.w);
+      // kCfUnroll edges per group in flight: all source vectors are requested before any is used (the kernel is bound
+      // by L2 gather latency — ncu long_scoreboard — so loads in flight per lane are what buys time)
+      for (uint32_t q = 0; q < n; q += 4 * kCfUnroll) {
+        float4 xu[kCfUnroll];
+        int32_t wu[kCfUnroll];
+        bool valid[kCfUnroll];
+#pragma unroll
+        for (int u = 0; u < kCfUnroll; ++u) {
+          const uint32_t idx = q + 4 * u + grp;
+          const uint32_t su = __shfl_sync(0xffffffffu, s, idx & 31);
+          wu[u] = __shfl_sync(0xffffffffu, w, idx & 31);
+          valid[u] = idx < n;
+          xu[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid[u] && holder) xu[u] = __ldg(reinterpret_cast<const float4*>(a.x_old + (size_t)su * kCfK) + sub);
+        }
+#pragma unroll
+        for (int u = 0; u < kCfUnroll; ++u) {  // ascending edge order inside the group: same numerics for any unroll
+          float dot = xu[u].x * xv.x;
+          dot = __fmaf_rn(xu[u].y, xv.y, dot);
+          dot = __fmaf_rn(xu[u].z, xv.z, dot);
+          dot = __fmaf_rn(xu[u].w, xv.w, dot);
+          dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+          dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+          dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+          const float err = valid[u] ? (float)wu[u] - dot : 0.f;
+          acc.x = __fmaf_rn(err, xu[u].x, acc.x);
+          acc.y = __fmaf_rn(err, xu[u].y, acc.y);
+          acc.z = __fmaf_rn(err, xu[u].z, acc.z);
+          acc.w = __fmaf_rn(err, xu[u].w, acc.w);
+        }
       }
     }
 #pragma unroll
