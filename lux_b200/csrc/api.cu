@@ -807,6 +807,18 @@ int luxb_init(luxb_graph* g) {
       LUXB_TRY(dmalloc((uint32_t**)&g->d_val[0], g->nv));
       LUXB_TRY(dmalloc(&g->d_cur, g->n_part));
       LUXB_TRY(build_push_csr(g));
+      {  // hot-packed label copies for the pull sweeps (same layout as PageRank; refreshed before every pull sweep)
+        LUXB_TRY(dmalloc(&g->d_deg, g->nv));
+        LUXB_CUDA(cudaMemsetAsync(g->d_deg, 0, (size_t)g->nv * 4, g->stream));
+        hist_src_kernel<<<grid, 256, 0, g->stream>>>(g->d_src, g->e_part, g->d_deg);
+        LUXB_CUDA(cudaGetLastError());
+        if (g->P > 1) LUXB_NCCL(nccl().AllReduce(g->d_deg, g->d_deg, g->nv, ncclUint32, ncclSum, g->comm, g->stream));
+        LUXB_TRY(build_hot_layout(g));
+        if (g->hot_n) {
+          LUXB_TRY(dmalloc((uint32_t**)&g->d_hot, g->hot_n));
+          LUXB_TRY(set_l2_persisting_window(g, g->d_hot, (size_t)g->hot_n * 4));
+        }
+      }
       g->big_capacity = (uint32_t)std::min<uint64_t>(g->e_part / kPushBigDegree + 1024, 0x7FFFFFFFull);
       LUXB_TRY(dmalloc((PushArgs::BigSeg**)&g->d_big_list, g->big_capacity));
       LUXB_TRY(dmalloc(&g->d_fq_all, g->fq_total));
@@ -1067,7 +1079,11 @@ static int label_iteration(luxb_graph* g) {
 
   if (pull) {
     typename Prog::Params prm{0};
-    LUXB_TRY(launch_pull<Prog>(g, lab, lab, 0, g->d_src, g->d_cur, prm, -1));
+    if (g->hot_n) {
+      hot_refresh_kernel<uint32_t><<<grid_for(g->hot_n, 256, g->num_sms * 8), 256, 0, g->stream>>>((uint32_t*)g->d_hot, lab, g->d_hot_order, 0, g->hot_n);
+      g->stats.kernel_launches++;
+    }
+    LUXB_TRY(launch_pull<Prog>(g, lab, (const uint32_t*)g->d_hot, g->hot_n, g->hot_n ? g->d_src_gather : g->d_src, g->d_cur, prm, -1));
     g->stats.edges_processed += g->e_part;
     g->stats.pull_iterations++;
   } else if (g->n_part && old_size) {
