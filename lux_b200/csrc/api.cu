@@ -745,6 +745,8 @@ static int build_hot_layout(luxb_graph* g) {
   return 0;
 }
 
+static int allgather_slices(luxb_graph* g, void* replica, size_t elem_bytes);
+
 int luxb_init(luxb_graph* g) {
   LUXB_ARG(g != nullptr, "graph is NULL");
   if (g->inited) { set_error("luxb_init called twice"); return LUXB_ERR_STATE; }
@@ -828,6 +830,13 @@ int luxb_init(luxb_graph* g) {
       LUXB_CUDA(cudaMallocHost(&g->h_hdr, 2 * LUXB_MAX_PARTS * 4));
       LUXB_CUDA(cudaMallocHost(&g->h_scratch, 64));
       LUXB_TRY(reset_label_state(g, false));
+      if (g->P > 1) {
+        // warm the communicator with the collectives the hot loop uses (NCCL sets up channels lazily, ~1 s for the
+        // first large grouped broadcast at 8 ranks): re-broadcasting the identical initial labels is a no-op
+        LUXB_NCCL(nccl().AllGather(g->d_fq_new, g->d_hdr_all, 8, ncclUint8, g->comm, g->stream));
+        LUXB_TRY(allgather_slices(g, g->d_val[0], 4));
+        LUXB_CUDA(cudaStreamSynchronize(g->stream));
+      }
       break;
     }
   }
