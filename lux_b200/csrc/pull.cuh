@@ -9,8 +9,8 @@
 // divergent 4-byte gathers) never idles.  Per warp tile:
 //   1. a producer warp streams the row_end words and source ids of kWarps consecutive warp tiles (one "super-tile")
 //      into a shared-memory ring with two TMA bulk copies (cp.async.bulk -> UBLKCP) behind a full/empty mbarrier
-//      pair per stage — measured: ~1 small bulk copy per 400 cycles per SM, so copies must be >= 10 KB to stay off
-//      the critical path.  L2 evict-first: streamed data must not displace the value array.  Consumer warps only
+//      pair per stage — measured: ~1 small bulk copy per 400 cycles per SM, so one copy pair serves 8 warp tiles
+//      (~7 KB) instead of one (per-warp copies made the kernel 2-4x slower).  L2 evict-first: streamed data must not displace the value array.  Consumer warps only
 //      meet at these mbarriers and may drift kStages-1 super-tiles apart;
 //   2. every lane finds its merge-path start by binary search over <= W row_end words in shared memory, then issues
 //      its (up to kIPT) gathers x[src] back to back on the read-only path — values land in REGISTERS in the order
