@@ -1456,6 +1456,7 @@ void luxb_close(luxb_graph* g) {
   }
   cudaSetDevice(g->cfg.device);
   if (g->stream) cudaStreamSynchronize(g->stream);
+  if (g->d_hot) cudaCtxResetPersistingL2Cache();  // release the lines pinned for the hot copies
   if (g->p2p_ready)
     for (int p = 0; p < g->P; ++p)
       if (p != g->cfg.rank)
