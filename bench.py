@@ -290,7 +290,7 @@ def main():
                 "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
                 "note": "traffic: see profiles/ (ncu dram__bytes_read.sum + dram__bytes_write.sum)"}
     prof = os.path.join(ROOT, "profiles", "latest_traffic.json")
-    if os.path.exists(prof):
+    if os.path.exists(prof) and world == 1:  # the ncu capture is of the 1-GPU launch
         try:
             roofline["traffic"] = json.load(open(prof)).get(workload)
         except Exception:  # noqa: BLE001
