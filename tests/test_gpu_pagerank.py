@@ -65,6 +65,22 @@ def test_pagerank_from_lux_file(tmp_path):
         assert_close(g.values(), O.pagerank(row_end, src, 3))
 
 
+def test_pagerank_one_step_rmat22_many_fixup_blocks():
+    """RMAT-22: 318 K warp tiles -> 1 242 fix-up blocks, i.e. more than the 1 024 threads of pull_fixup_blocks_kernel
+    (serial chunks of 2 blocks per thread), and a hub whose in-edge list spans several fix-up blocks."""
+    scale = 22
+    nv, ne = 1 << scale, 16 << scale
+    with L.LuxGraph.from_rmat(scale, nv, ne, 27) as g:
+        row_end, src = g.local_csc()
+        g.init()
+        g.iterate(2)
+        x2 = g.values()
+        deg = g.out_degree()
+        g.iterate(1)
+        x3 = g.values()
+    assert_close(x3, O.pagerank_iter(row_end, src, deg, x2))
+
+
 def test_pagerank_one_step_property_rmat20():
     """Size-independent check usable at full scale: after k iterations on the device, one more device iteration
     must equal one oracle iteration applied to the device's own state; plus the linearity checksum
