@@ -22,6 +22,10 @@ import sys
 import threading
 import time
 
+# OpenMP placement of the CPU legs (oracle): spread threads over all cores / NUMA nodes, set before libgomp is loaded
+os.environ.setdefault("OMP_PROC_BIND", "spread")
+os.environ.setdefault("OMP_PLACES", "cores")
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -44,6 +48,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     return ap.parse_args()
 
 
@@ -113,43 +118,57 @@ def dist_env():
     return rank, world, local
 
 
-def cpu_baseline_pagerank(row_end, src, deg, x_old, steps, target_s=6.0):
-    """Oracle (CPU port of the reference semantics) on all host cores over a bounded sample: a prefix range of
-    destination vertices sized to ~target_s seconds per step.  Returns (MTEPS, cores, sample description, secs)."""
+def numa_nodes():
+    try:
+        return len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()])
+    except OSError:
+        return None
+
+
+def oracle_sample(scale, nv, ne, frac_log2, must_cover=(), block_shift=14, seed_sel=12345):
+    """A bounded sample of the workload built by the ORACLE's own generator (nothing of the product): destination
+    blocks of 2^block_shift consecutive vertices chosen pseudo-randomly (1 in 2^frac_log2 — the representative part,
+    identical for every caller) plus the blocks containing every id in must_cover (partition boundaries, hubs).
+    Returns (blk, deg, description, blk_random) where blk_random is the representative part alone."""
     import oracle as O
-    nv, ne = len(row_end), len(src)
-    out = np.zeros(nv, np.float32)
+    block_shift = min(block_shift, max(scale - 6, 0))
+    n_blocks = ((nv - 1) >> block_shift) + 1
+    rng = np.random.default_rng(seed_sel)
+    rnd = rng.integers(0, 1 << frac_log2, n_blocks) == 0
+    sel = rnd.astype(np.uint8)
+    for v in must_cover:
+        if 0 <= v < nv:
+            sel[int(v) >> block_shift] = 1
+    blk = O.rmat_blocks(scale, nv, ne, SEED, block_shift, sel, want_deg=True)
+    blk["desc"] = "%d destination blocks of %d vertices (%d vertices, %d of %d edges), oracle generator" % (
+        int(sel.sum()), 1 << block_shift, len(blk["vid"]), len(blk["src"]), ne)
+    # the representative part: keep the vertices whose block was drawn at random
+    keep_v = rnd[blk["vid"].astype(np.int64) >> block_shift]
+    if keep_v.all():
+        sub = blk
+    else:
+        ends = blk["row_end"].astype(np.int64)
+        begins = np.concatenate([[0], ends[:-1]])
+        cnt = (ends - begins)[keep_v]
+        keep_e = np.repeat(keep_v, ends - begins)
+        sub = dict(vid=blk["vid"][keep_v], row_end=np.cumsum(cnt, dtype=np.uint64), src=np.ascontiguousarray(blk["src"][keep_e]),
+                   deg=blk["deg"])
+    sub["desc"] = "%d pseudo-random destination blocks of %d vertices (1 in %d; %d vertices, %d of %d edges), oracle generator" % (
+        int(rnd.sum()), 1 << block_shift, 1 << frac_log2, len(sub["vid"]), len(sub["src"]), ne)
+    return blk, blk["deg"], blk["desc"], sub
 
-    def run(v_hi):
+
+def time_oracle_sample(nv, blk, deg, x_old, budget_s, min_runs=3, max_runs=200):
+    """Oracle PageRank iterations over the sample on all host cores; returns (MTEPS, cores, per-run seconds)."""
+    import oracle as O
+    out = np.empty(len(blk["vid"]), np.float32)
+    O.pagerank_iter_compact(nv, blk, deg, x_old, out=out)  # warm-up (page faults of `out`, thread pool)
+    times, t_all = [], time.perf_counter()
+    while len(times) < min_runs or (time.perf_counter() - t_all < budget_s and len(times) < max_runs):
         t0 = time.perf_counter()
-        O.pagerank_iter(row_end, src, deg, x_old, 0, v_hi, out=out)
-        return time.perf_counter() - t0
-
-    # size the sample on a small prefix, then pick the thread count (all logical CPUs or half of them — SMT siblings
-    # often hurt a latency-bound gather) ON THE SAMPLE ITSELF: prefix ranges are hub-heavy and mislead
-    probe_hi = int(np.searchsorted(row_end, ne // 32, side="left"))
-    probe_hi = min(max(probe_hi, 0), nv - 1)
-    e_probe = int(row_end[probe_hi])
-    ncpu = os.cpu_count() or 1
-    O.set_num_threads(ncpu)
-    run(probe_hi)
-    rate = e_probe / max(min(run(probe_hi), run(probe_hi)), 1e-9)
-    want_edges = min(ne, int(rate * target_s))
-    v_hi = nv - 1 if want_edges >= ne else int(np.searchsorted(row_end, want_edges, side="left"))
-    v_hi = min(max(v_hi, probe_hi), nv - 1)
-    edges = int(row_end[v_hi])
-    best_t, best_n = None, ncpu
-    for nthr in sorted({ncpu, max(1, ncpu // 2)}, reverse=True):
-        O.set_num_threads(nthr)
-        t = run(v_hi)
-        if best_t is None or t < best_t:
-            best_t, best_n = t, nthr
-    O.set_num_threads(best_n)
-    times = [run(v_hi) for _ in range(max(steps, 1))]
-    best = float(np.median(times))
-    desc = "1 PageRank iteration over destination vertices [0,%d] = %d of %d edges, median of %d runs" % (
-        v_hi, edges, ne, len(times))
-    return edges / best / 1e6, O.num_threads(), desc, times
+        O.pagerank_iter_compact(nv, blk, deg, x_old, out=out)
+        times.append(time.perf_counter() - t0)
+    return len(blk["src"]) / float(np.median(times)) / 1e6, O.num_threads(), times
 
 
 def main():
@@ -166,33 +185,47 @@ def main():
                   (4 * ne + 8 * nv) / args.gpus / 1e9, 4 * nv / 1e6),
               "parallelism": "dst-range partitions x%d (reference greedy edge-balanced split)" % args.gpus}
 
-    import lux_b200 as L
-
     if args.impl == "reference":
         if rank != 0:
             return 0
-        # input synthesis only: the device generator builds the same RMAT CSC our arm uses, it is copied to the host
-        # and the library handle is closed before anything is timed.  The timed path is the CPU oracle alone.
-        with L.LuxGraph.from_rmat(scale, nv, ne, SEED, device=0) as g:
-            row_end, src = g.local_csc()
-            g.init()
-            deg = g.out_degree()
-            x0 = g.values()
+        # The reference has no CPU compute path and cannot be built (Legion missing): this arm times the
+        # oracle port on all host cores.  Input: the ORACLE's own generator (nothing of the product is loaded here);
+        # a step = ITERS_PER_STEP PageRank iterations over a bounded, representative sample of the destination vertices.
         import oracle as O
+        t0 = time.perf_counter()
+        _, deg, _, blk = oracle_sample(scale, nv, ne, frac_log2=4)
+        desc = blk["desc"]
+        x0 = O.pagerank_init(deg)
+        t_gen = time.perf_counter() - t0
+        out = np.empty(len(blk["vid"]), np.float32)
+        edges = len(blk["src"])
+
+        def step():
+            t = time.perf_counter()
+            for _ in range(ITERS_PER_STEP):
+                O.pagerank_iter_compact(nv, blk, deg, x0, out=out)
+            return time.perf_counter() - t
+
         for _ in range(args.warmup):
-            pass
-        mteps, cores, desc, times = cpu_baseline_pagerank(row_end, src, deg, x0, args.steps + args.warmup)
-        times = times[args.warmup:] if len(times) > args.warmup else times
-        ms = 1e3 * float(np.mean(times))
+            step()
+        times = [step() for _ in range(args.steps)]
+        total = float(np.sum(times))
+        mteps = edges * ITERS_PER_STEP * args.steps / total / 1e6
+        sample = "%d iterations per step over %s" % (ITERS_PER_STEP, desc)
         line = {"impl": "reference", "metric": "MTEPS", "value": mteps, "unit": "MTEPS", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": mteps, "unit": "MTEPS", "cores": cores, "kind": "port", "sample": desc},
+                "cpu_baseline": {"value": mteps, "unit": "MTEPS", "cores": O.num_threads(), "kind": "port", "sample": sample,
+                                 "numa_nodes": numa_nodes(), "omp": {k: os.environ.get(k) for k in ("OMP_PROC_BIND", "OMP_PLACES")},
+                                 "per_step_seconds": times},
                 "e2e": {"value": mteps, "unit": "MTEPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0,
-                "note": "reference has no CPU compute path and needs Legion (SURVEY §8c): the oracle port is timed"}
+                "gpu_launches": 0, "input_seconds": t_gen,
+                "note": "reference has no CPU compute path and needs Legion (SURVEY §8c): the oracle port is timed; "
+                        "input generated by the oracle itself (libluxb is not loaded in this arm)"}
         print(json.dumps(line))
         return 0
+
+    import lux_b200 as L
 
     # ------------------------------------------------------------------------------------------------ ours
     import torch
@@ -322,13 +355,37 @@ def main():
         except Exception as e:  # noqa: BLE001
             ref_gpu = {"unavailable": repr(e)[:200]}
 
-    cpu_base = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        row_end, src = g.local_csc()
-        deg = g.out_degree()
-        x0 = g.values()
-        mteps, cores, desc, _ = cpu_baseline_pagerank(row_end, src, deg, x0, 3)
-        cpu_base = {"value": mteps, "unit": "MTEPS", "cores": cores, "kind": "port", "sample": desc}
+    # ---- parity at this N (after the timed region): the device's state x_k, ONE more device iteration, and on rank 0
+    # one ORACLE iteration from x_k over a sample of destination blocks generated by the oracle itself — pseudo-random
+    # blocks plus the blocks around every partition boundary and vertex 0 (hubs), so every rank's slice and therefore
+    # the exchange is covered.  The same sample feeds the CPU baseline at N = 1. ----
+    parity, cpu_base = None, None
+    if not args.no_parity:
+        x_k = g.values() if rank == 0 else None
+        g.iterate(1)
+        x_k1 = g.values() if rank == 0 else None
+        if rank == 0:
+            import oracle as O
+            b = g.bounds()
+            cover = [0, nv - 1]
+            for p in range(world):
+                cover += [int(b["row_left"][p]), int(b["row_right"][p]) & 0xFFFFFFFF]
+            blk, deg_o, desc, blk_rnd = oracle_sample(scale, nv, ne, frac_log2=4, must_cover=cover)
+            ref = O.pagerank_iter_compact(nv, blk, deg_o, x_k)
+            got = x_k1[blk["vid"]]
+            rel = np.abs(got.astype(np.float64) - ref.astype(np.float64)) / np.maximum(np.abs(ref.astype(np.float64)), 1e-300)
+            deg_dev_ok = None
+            if world == 1:
+                deg_dev_ok = bool(np.array_equal(g.out_degree(), deg_o))
+            parity = {"max_rel_err": float(rel.max()), "tolerance": 1e-6, "ok": bool(rel.max() <= 1e-6),
+                      "checked_vertices": int(len(ref)), "checked_edges": int(len(blk["src"])), "sample": desc,
+                      "partitions_covered": world, "device_out_degrees_equal_oracle": deg_dev_ok,
+                      "what": "device x_k -> one device iteration vs one oracle iteration (fp64 sums) on the sample"}
+            if world == 1 and not args.no_cpu_baseline:
+                mteps, cores, times = time_oracle_sample(nv, blk_rnd, deg_o, x_k, budget_s=12.0)
+                cpu_base = {"value": mteps, "unit": "MTEPS", "cores": cores, "kind": "port", "numa_nodes": numa_nodes(),
+                            "sample": "1 PageRank iteration over %s (the reference arm's sample), median of %d runs" % (
+                                blk_rnd["desc"], len(times))}
     g.close()
 
     if rank == 0:
@@ -336,7 +393,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": 1e3 * dev_s_max / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "e2e": e2e, "gpu_launches": total_launches, "roofline": roofline, "cpu_baseline": cpu_base,
-                "reference_gpu_replay": ref_gpu, "clocks": clocks, "wall_ms_per_step": 1e3 * wall_s_max / args.steps, "build_seconds": t_build,
+                "parity": parity, "reference_gpu_replay": ref_gpu, "clocks": clocks, "wall_ms_per_step": 1e3 * wall_s_max / args.steps, "build_seconds": t_build,
                 "exchange": args.exchange if world > 1 else "none",
                 "roofline_whole_step": {"algorithmic_GBps_per_gpu": (8 * ne + 16 * nv) * ITERS_PER_STEP * args.steps
                                         / world / dev_s_max / 1e9, "frac": (8 * ne + 16 * nv) * ITERS_PER_STEP

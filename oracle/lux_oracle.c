@@ -17,7 +17,9 @@
  *   (2) tests/golden/hand5.lux.hex — bytes written by the reference's tools/converter.cc;
  *   (3) hand-derived answers and an independent numpy restatement (tests/test_oracle.py).
  * col_filter is NOT pinned by execution: the reference kernel is racy and mis-indexed; the oracle
- * restates the intended math and is pinned only by (3).
+ * restates the intended math and is pinned by (3) and MATHEMATICALLY by tests/test_oracle.py::
+ * test_colfilter_step_is_minus_gamma_times_the_gradient_...: lo_cf_iter's step equals -GAMMA times the
+ * finite-difference gradient of the regularised squared error the reference's constants define (col_filter/app.h:26-28).
  *
  * Every function cites the reference file:line it restates.
  */
@@ -157,6 +159,107 @@ int lo_gen_rmat_csc(int scale, V_ID nv, E_ID ne, uint64_t seed, E_ID* row_end, V
   radix_sort_u64(keys, ne, 64);
   keys_to_csc(keys, ne, nv, row_end, src);
   free(keys);
+  return 0;
+}
+
+/* ---- sampled CSC of the RMAT graph: only the destination BLOCKS (2^block_shift consecutive ids) flagged in
+ * block_sel are materialised, in ascending block order ("compact" local vertex numbering).  Used at full scale
+ * (RMAT-27) by bench.py's CPU baseline / reference arm and its N-GPU parity check, where building the whole CSC on
+ * the host would cost minutes: one OpenMP scan of the edge counter per pass, arrays first-touched by the threads
+ * that fill them (NUMA-interleaved).
+ *   pass 1  lo_rmat_blocks_count: indeg_local[i] (per compact vertex) and, if deg != NULL, the global out-degrees
+ *           (pull_scan_task_impl, pull_model.inl:333-343);
+ *   pass 2  lo_rmat_blocks_fill : src[] for the compact vertices, canonical order (ascending source inside a vertex). */
+static inline int64_t block_local_base(int block_shift, const int64_t* block_base, V_ID d) {
+  return block_base[d >> block_shift];
+}
+
+int lo_rmat_blocks_count(int scale, V_ID nv, E_ID ne, uint64_t seed, int block_shift, const uint8_t* block_sel,
+                         V_ID* deg /* [nv] or NULL */, V_ID* indeg_local /* [n_local] */, uint64_t n_local) {
+  const uint64_t n_blocks = (((uint64_t)nv - 1) >> block_shift) + 1;
+  int64_t* block_base = (int64_t*)malloc(n_blocks * sizeof(int64_t));
+  if (!block_base) return -1;
+  int64_t run = 0;
+  for (uint64_t b = 0; b < n_blocks; b++) {
+    if (block_sel[b]) {
+      uint64_t lo = b << block_shift, hi = lo + (1ull << block_shift);
+      if (hi > nv) hi = nv;
+      block_base[b] = run;
+      run += (int64_t)(hi - lo);
+    } else block_base[b] = -1;
+  }
+  if ((uint64_t)run != n_local) { free(block_base); return -2; }
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < (int64_t)n_local; i++) indeg_local[i] = 0;
+  if (deg) {
+#pragma omp parallel for schedule(static)
+    for (int64_t v = 0; v < (int64_t)nv; v++) deg[v] = 0;
+  }
+  const uint64_t mask = (1ull << block_shift) - 1;
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < (int64_t)ne; i++) {
+    V_ID s, d;
+    lo_rmat_edge(seed, (uint64_t)i, scale, nv, &s, &d);
+    if (deg) {
+#pragma omp atomic
+      deg[s]++;
+    }
+    int64_t base = block_local_base(block_shift, block_base, d);
+    if (base >= 0) {
+#pragma omp atomic
+      indeg_local[base + (int64_t)(d & mask)]++;
+    }
+  }
+  free(block_base);
+  return 0;
+}
+
+static int cmp_vid(const void* a, const void* b) {
+  V_ID x = *(const V_ID*)a, y = *(const V_ID*)b;
+  return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+int lo_rmat_blocks_fill(int scale, V_ID nv, E_ID ne, uint64_t seed, int block_shift, const uint8_t* block_sel,
+                        const E_ID* row_end_local /* [n_local] inclusive scan of indeg_local */, uint64_t n_local,
+                        V_ID* src /* [row_end_local[n_local-1]] */) {
+  const uint64_t n_blocks = (((uint64_t)nv - 1) >> block_shift) + 1;
+  int64_t* block_base = (int64_t*)malloc(n_blocks * sizeof(int64_t));
+  E_ID* cursor = (E_ID*)malloc((n_local ? n_local : 1) * sizeof(E_ID));
+  if (!block_base || !cursor) { free(block_base); free(cursor); return -1; }
+  int64_t run = 0;
+  for (uint64_t b = 0; b < n_blocks; b++) {
+    if (block_sel[b]) {
+      uint64_t lo = b << block_shift, hi = lo + (1ull << block_shift);
+      if (hi > nv) hi = nv;
+      block_base[b] = run;
+      run += (int64_t)(hi - lo);
+    } else block_base[b] = -1;
+  }
+  if ((uint64_t)run != n_local) { free(block_base); free(cursor); return -2; }
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < (int64_t)n_local; i++) cursor[i] = i == 0 ? 0 : row_end_local[i - 1];
+  const uint64_t mask = (1ull << block_shift) - 1;
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < (int64_t)ne; i++) {
+    V_ID s, d;
+    lo_rmat_edge(seed, (uint64_t)i, scale, nv, &s, &d);
+    int64_t base = block_local_base(block_shift, block_base, d);
+    if (base >= 0) {
+      E_ID pos;
+      E_ID* c = &cursor[base + (int64_t)(d & mask)];
+#pragma omp atomic capture
+      pos = (*c)++;
+      src[pos] = s;
+    }
+  }
+  /* canonical order inside each vertex: ascending source (the slots were claimed in thread-arrival order) */
+#pragma omp parallel for schedule(dynamic, 1024)
+  for (int64_t i = 0; i < (int64_t)n_local; i++) {
+    E_ID b = i == 0 ? 0 : row_end_local[i - 1], e = row_end_local[i];
+    if (e - b > 1) qsort(src + b, (size_t)(e - b), sizeof(V_ID), cmp_vid);
+  }
+  free(block_base);
+  free(cursor);
   return 0;
 }
 
@@ -316,7 +419,25 @@ void lo_out_degree(V_ID nv, E_ID ne, const V_ID* src, V_ID* deg) {
 
 void lo_pagerank_init(V_ID nv, const V_ID* deg, float* x) {
   float rank = 1.0f / nv; /* pagerank_gpu.cu:255 */
-  for (V_ID v = 0; v < nv; v++) x[v] = deg[v] == 0 ? rank : rank / deg[v];
+#pragma omp parallel for schedule(static)
+  for (int64_t v = 0; v < (int64_t)nv; v++) x[v] = deg[v] == 0 ? rank : rank / deg[v];
+}
+
+/* the same iteration over a COMPACT set of destination vertices (lo_rmat_blocks_*): local vertex i has global id
+ * vid[i] and in-edges src[row_end_local[i-1] .. row_end_local[i]); x_old / deg are indexed globally, x_new_local by i */
+void lo_pagerank_iter_compact(V_ID nv, uint64_t n_local, const E_ID* row_end_local, const V_ID* src, const V_ID* vid,
+                              const V_ID* deg, const float* x_old, float* x_new_local) {
+  const float init_rank = (1 - LO_ALPHA) / nv; /* pagerank_gpu.cu:144 */
+#pragma omp parallel for schedule(dynamic, 4096)
+  for (int64_t i = 0; i < (int64_t)n_local; i++) {
+    E_ID b = i == 0 ? 0 : row_end_local[i - 1], e = row_end_local[i];
+    double s = 0.0;
+    for (E_ID k = b; k < e; k++) s += (double)x_old[src[k]];
+    float y = fmaf(LO_ALPHA, (float)s, init_rank);
+    V_ID dg = deg[vid[i]];
+    if (dg != 0) y = y / (float)dg;
+    x_new_local[i] = y;
+  }
 }
 
 /* one iteration over destination vertices [v_lo, v_hi]; x_new indexed globally */

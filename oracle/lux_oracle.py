@@ -72,6 +72,40 @@ def gen_rmat_csc(scale, nv, ne, seed):
     return row_end, src
 
 
+def rmat_blocks(scale, nv, ne, seed, block_shift, block_sel, want_deg=True):
+    """Sampled CSC of the RMAT graph: only destination blocks (2^block_shift ids) flagged in block_sel, compact
+    numbering.  Returns dict(vid u32[n_local], row_end u64[n_local] (relative, inclusive), src u32[], deg u32[nv]|None).
+    Two parallel scans of the edge counter; nothing of the product is involved."""
+    block_sel = np.ascontiguousarray(block_sel, np.uint8)
+    n_blocks = ((nv - 1) >> block_shift) + 1
+    assert len(block_sel) == n_blocks
+    blocks = np.nonzero(block_sel)[0].astype(np.int64)
+    parts = [np.arange(b << block_shift, min((b + 1) << block_shift, nv), dtype=np.uint32) for b in blocks]
+    vid = np.concatenate(parts) if parts else np.zeros(0, np.uint32)
+    n_local = len(vid)
+    deg = np.empty(nv, np.uint32) if want_deg else None
+    indeg = np.empty(max(n_local, 1), np.uint32)[:n_local]
+    rc = lib().lo_rmat_blocks_count(C.c_int(scale), C.c_uint32(nv), C.c_uint64(ne), C.c_uint64(seed), C.c_int(block_shift),
+                                    _p(block_sel), _p(deg), _p(indeg), C.c_uint64(n_local))
+    assert rc == 0, rc
+    row_end = np.cumsum(indeg, dtype=np.uint64)
+    ne_local = int(row_end[-1]) if n_local else 0
+    src = np.empty(max(ne_local, 1), np.uint32)[:ne_local]
+    rc = lib().lo_rmat_blocks_fill(C.c_int(scale), C.c_uint32(nv), C.c_uint64(ne), C.c_uint64(seed), C.c_int(block_shift),
+                                   _p(block_sel), _p(row_end), C.c_uint64(n_local), _p(src))
+    assert rc == 0, rc
+    return dict(vid=vid, row_end=row_end, src=src, deg=deg)
+
+
+def pagerank_iter_compact(nv, blk, deg, x_old, out=None):
+    """One oracle PageRank iteration over the compact vertex set of rmat_blocks(); returns x_new[vid] (local order)."""
+    n_local = len(blk["vid"])
+    x_new = out if out is not None else np.empty(n_local, np.float32)
+    lib().lo_pagerank_iter_compact(C.c_uint32(nv), C.c_uint64(n_local), _p(blk["row_end"]), _p(blk["src"]), _p(blk["vid"]),
+                                   _p(deg), _p(x_old), _p(x_new))
+    return x_new
+
+
 def gen_bipartite_csc(users, items, ratings, seed):
     nv, ne = users + items, 2 * ratings
     row_end = np.empty(nv, np.uint64)

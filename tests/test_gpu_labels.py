@@ -63,3 +63,33 @@ def test_device_generated_rmat18_cc_and_sssp():
         assert g.check() == 0
     ref = O.label_run(O.APP_CC, row_end, src, P=1)
     assert it == ref["iters"] and np.array_equal(lab, ref["labels"])
+
+
+@pytest.mark.parametrize("app,oapp", [(L.APP_CC, O.APP_CC), (L.APP_SSSP, O.APP_SSSP)])
+def test_check_counts_mistakes_like_the_reference_predicate(app, oapp):
+    """luxb_check must COUNT violations of the reference's predicate (components_gpu.cu:786-790: label[dst] <
+    label[src]; sssp_gpu.cu:792-796: label[src] != nv and label[dst] > label[src] + 1), not merely return 0 on a
+    correct answer: corrupt k random labels of a converged result and compare the count with the oracle's."""
+    row_end, src = rmat(14)
+    nv = len(row_end)
+    ref = O.label_run(oapp, row_end, src, P=1, start=0)["labels"]
+    rng = np.random.default_rng(11)
+    with L.LuxGraph.from_csc(row_end, src, app=app, start=0) as g:
+        g.init()
+        g.run_to_convergence()
+        assert g.check() == 0
+        for k in (1, 7, 300):
+            bad = ref.copy()
+            idx = rng.choice(nv, k, replace=False)
+            if app == L.APP_CC:
+                bad[idx] = rng.integers(0, nv, k).astype(np.uint32)       # arbitrary (mostly too small) labels
+            else:
+                bad[idx] = (bad[idx].astype(np.int64) + rng.integers(2, 9, k)).clip(0, nv).astype(np.uint32)  # too far
+            want = O.label_check(oapp, row_end, src, bad)
+            g.set_values(bad)
+            got = g.check()
+            assert got == want, (k, got, want)
+            if k >= 7:
+                assert want > 0
+        g.set_values(ref)
+        assert g.check() == 0

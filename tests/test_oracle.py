@@ -268,6 +268,46 @@ def test_colfilter_matches_numpy_restatement():
     assert np.allclose(got, x, rtol=1e-6, atol=0)
 
 
+def test_colfilter_step_is_minus_gamma_times_the_gradient_of_the_regularised_squared_error():
+    """Mathematical pin of the col_filter oracle (the reference kernel is racy and mis-indexed, SURVEY §2.2, so it
+    cannot be pinned by execution).  What the reference INTENDS (colfilter_gpu.cu:83-100 with LAMBDA / GAMMA of
+    col_filter/app.h:26-27) is one Jacobi gradient-descent step on
+        L_v(x_v) = 1/2 * sum_{(u,w) in in(v)} (w - <x_u, x_v>)^2 + 1/2 * LAMBDA * |x_v|^2        (x_u held fixed)
+    i.e. x_v' - x_v = -GAMMA * grad L_v(x_v).  The gradient is taken here by CENTRAL FINITE DIFFERENCES of L_v in
+    float64 — no line of this test restates the update formula."""
+    lam, gamma = 1e-3, 3.5e-7
+    row_end, src, w = O.gen_bipartite_csc(300, 40, 20000, 5)
+    nv = len(row_end)
+    rng = np.random.default_rng(3)
+    x = (0.1 + 0.4 * rng.random((nv, 20))).astype(np.float32)  # not the uniform start: every factor gets its own slope
+    x_new = O.cf_iter(row_end, src, w, x)
+    starts = np.concatenate([[0], row_end[:-1]]).astype(np.int64)
+    x64 = x.astype(np.float64)
+
+    def loss(v, xv):
+        b, e = starts[v], int(row_end[v])
+        err = w[b:e].astype(np.float64) - x64[src[b:e]] @ xv
+        return 0.5 * np.dot(err, err) + 0.5 * lam * np.dot(xv, xv)
+
+    checked = 0
+    for v in list(range(0, 300, 37)) + list(range(300, 340, 5)):  # users (degree ~67) and items (degree ~500)
+        if int(row_end[v]) - starts[v] == 0:
+            continue
+        grad = np.zeros(20)
+        for k in range(20):
+            h = 1e-5
+            xp, xm = x64[v].copy(), x64[v].copy()
+            xp[k] += h
+            xm[k] -= h
+            grad[k] = (loss(v, xp) - loss(v, xm)) / (2 * h)
+        step = (x_new[v].astype(np.float64) - x64[v]) / (-gamma)
+        # x' - x is a difference of f32 numbers near 0.3: resolution ulp(0.5)/gamma ~ 0.1 in gradient units
+        assert np.allclose(step, grad, rtol=2e-3, atol=0.1), (v, np.abs(step - grad).max(), np.abs(grad).max())
+        assert np.abs(grad).max() > 5  # the comparison is not vacuous (atol is < 2 % of it)
+        checked += 1
+    assert checked >= 10
+
+
 # ---- generators ----------------------------------------------------------------------------------------------
 def test_rmat_generator_properties():
     scale, nv = 12, 3000
