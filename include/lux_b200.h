@@ -155,6 +155,9 @@ typedef struct {
   uint32_t last_frontier_type; /* this rank's frontier representation after the last iteration */
   double dominant_kernel_seconds;   /* with kernel timing on: device time inside the gather kernel(s) only */
   uint64_t dominant_kernel_launches;
+  uint64_t panel_edges;      /* PageRank: local edges swept by the source-blocked (shared-memory) kernel; 0 = plain sweep */
+  uint32_t panel_hubs;       /*   hub destinations of this partition */
+  uint32_t panel_blocks;     /*   hot source blocks */
 } luxb_stats_t;
 int luxb_stats(const luxb_graph* g, luxb_stats_t* out);
 /* Per-iteration trace of push apps (global active count, direction) for parity tests; returns #entries copied. */

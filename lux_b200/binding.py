@@ -35,7 +35,8 @@ class Stats(C.Structure):
     _fields_ = [("loop_seconds", C.c_double), ("iterations", C.c_uint64), ("edges_processed", C.c_uint64),
                 ("pull_iterations", C.c_uint64), ("kernel_launches", C.c_uint64), ("last_active", C.c_uint64),
                 ("last_frontier_type", C.c_uint32), ("dominant_kernel_seconds", C.c_double),
-                ("dominant_kernel_launches", C.c_uint64)]
+                ("dominant_kernel_launches", C.c_uint64), ("panel_edges", C.c_uint64), ("panel_hubs", C.c_uint32),
+                ("panel_blocks", C.c_uint32)]
 
 
 class DeviceView(C.Structure):

@@ -12,41 +12,35 @@
 #include "build.cuh"
 #include "cf.cuh"
 #include "pull.cuh"
+#include "panel.cuh"
 #include "push.cuh"
 #include "runtime.cuh"
 
 using namespace luxb;
-// dev aid: LUXB_PHASE_TIMING=1 prints the mean device time of each phase of a PageRank iteration at luxb_close
-struct PhaseTimer {
-  bool on = false;
-  std::vector<cudaEvent_t> ev;
-  std::vector<int> tag;
-  double sum[8] = {0};
-  long cnt = 0;
-  const char* name[8] = {"pull_tile", "fixup", "refresh", "push/exchange", "barrier", "", "", ""};
-};
-static PhaseTimer g_pt;
+static const char* const kPhaseName[8] = {"pull_tile", "fixup", "refresh", "push/exchange", "barrier", "panel", "combine", ""};
 static void pt_mark(luxb_graph* g, int tag) {
-  if (!g_pt.on) return;
+  PhaseTimer& pt = g->pt;
+  if (!pt.on) return;
   cudaEvent_t e;
   cudaEventCreate(&e);
   cudaEventRecord(e, g->stream);
-  g_pt.ev.push_back(e);
-  g_pt.tag.push_back(tag);
+  pt.ev.push_back(e);
+  pt.tag.push_back(tag);
 }
 static void pt_flush(luxb_graph* g) {
-  if (!g_pt.on || g_pt.ev.empty()) return;
+  PhaseTimer& pt = g->pt;
+  if (!pt.on || pt.ev.empty()) return;
   cudaStreamSynchronize(g->stream);
-  for (size_t i = 1; i < g_pt.ev.size(); ++i) {
-    if (g_pt.tag[i] < 0) continue;
+  for (size_t i = 1; i < pt.ev.size(); ++i) {
+    if (pt.tag[i] < 0) continue;
     float ms = 0;
-    cudaEventElapsedTime(&ms, g_pt.ev[i - 1], g_pt.ev[i]);
-    g_pt.sum[g_pt.tag[i]] += ms;
-    if (g_pt.tag[i] == 0) g_pt.cnt++;
+    cudaEventElapsedTime(&ms, pt.ev[i - 1], pt.ev[i]);
+    pt.sum[pt.tag[i]] += ms;
+    if (pt.tag[i] == 0) pt.cnt++;
   }
-  for (cudaEvent_t e : g_pt.ev) cudaEventDestroy(e);
-  g_pt.ev.clear();
-  g_pt.tag.clear();
+  for (cudaEvent_t e : pt.ev) cudaEventDestroy(e);
+  pt.ev.clear();
+  pt.tag.clear();
 }
 
 
@@ -172,6 +166,9 @@ static int graph_begin(const luxb_config* cfg, luxb_graph** out) {
   LUXB_CUDA(cudaEventCreate(&g->ev_begin));
   LUXB_CUDA(cudaEventCreate(&g->ev_end));
   LUXB_CUDA(cudaDeviceGetAttribute(&g->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
+  g->pull_ctas = kDefaultPullCtas;
+  if (const char* env = getenv("LUXB_PULL_CTAS")) g->pull_ctas = std::max(1, atoi(env));
+  if (const char* env = getenv("LUXB_PHASE_TIMING")) g->pt.on = atoi(env) != 0;
   return 0;
 }
 
@@ -221,7 +218,7 @@ static int finish_layout(luxb_graph* g) {
   LUXB_TRY(dmalloc(&g->d_carry_flag, (uint64_t)g->n_tiles + 1));
   LUXB_TRY(dmalloc((uint64_t**)&g->d_block_agg, (uint64_t)g->n_fix_blocks + 1));
   LUXB_TRY(dmalloc(&g->d_block_flag, (uint64_t)g->n_fix_blocks + 1));
-  LUXB_TRY(dmalloc(&g->d_counters, 8));
+  LUXB_TRY(dmalloc(&g->d_counters, 8));  // [0] edges scanned, [1] check mistakes, [2] pull tile counter, [3] big segments, [4] panel tile counter
   LUXB_CUDA(cudaMemsetAsync(g->d_counters, 0, 8 * sizeof(unsigned long long), g->stream));
   LUXB_CUDA(cudaStreamSynchronize(g->stream));
   return 0;
@@ -746,6 +743,7 @@ static int build_hot_layout(luxb_graph* g) {
 }
 
 static int allgather_slices(luxb_graph* g, void* replica, size_t elem_bytes);
+static int build_panel_layout(luxb_graph* g);
 
 int luxb_init(luxb_graph* g) {
   LUXB_ARG(g != nullptr, "graph is NULL");
@@ -762,6 +760,7 @@ int luxb_init(luxb_graph* g) {
       LUXB_CUDA(cudaGetLastError());
       if (g->P > 1) LUXB_NCCL(nccl().AllReduce(g->d_deg, g->d_deg, g->nv, ncclUint32, ncclSum, g->comm, g->stream));
       LUXB_TRY(build_hot_layout(g));
+      LUXB_TRY(build_panel_layout(g));
       g->ag_chunk = ((uint64_t)g->nv + g->P - 1) / g->P;  // equal chunks of the balanced all-gather
       g->ag_chunk = (g->ag_chunk + 31) & ~31ull;
       for (int k = 0; k < 2; ++k) LUXB_TRY(dmalloc((float**)&g->d_val[k], g->ag_chunk * g->P));
@@ -769,7 +768,9 @@ int luxb_init(luxb_graph* g) {
       LUXB_CUDA(cudaMemsetAsync(g->d_val[1], 0, (size_t)g->nv * 4, g->stream));
       if (g->hot_n) {
         g->hot_chunk = (((uint64_t)g->hot_n + g->P - 1) / g->P + 31) & ~31ull;
-        LUXB_TRY(dmalloc((float**)&g->d_hot, g->hot_chunk * g->P));
+        // + one whole table of slack: the panel kernel always bulk-loads full blocks (panel.cuh)
+        LUXB_TRY(dmalloc((float**)&g->d_hot, g->hot_chunk * g->P + 65536));
+        LUXB_CUDA(cudaMemsetAsync(g->d_hot, 0, (g->hot_chunk * g->P + 65536) * 4, g->stream));
         hot_refresh_kernel<float><<<grid_for(g->hot_n, 256, grid), 256, 0, g->stream>>>((float*)g->d_hot, (const float*)g->d_val[0], g->d_hot_order, 0, g->hot_n);
         LUXB_TRY(set_l2_persisting_window(g, g->d_hot, (size_t)g->hot_n * 4));
       }
@@ -870,63 +871,108 @@ static int p2p_barrier(luxb_graph* g) {
 }
 
 extern "C++" {
+// the partition's own CSC as a layout view (no ownership)
+static PullLayout base_layout(const luxb_graph* g, const uint32_t* src_idx) {
+  PullLayout L;
+  L.d_row_end = g->d_row_end;
+  L.d_row_end32 = g->d_row_end32;
+  L.d_src = const_cast<uint32_t*>(src_idx);
+  L.d_tile_v = g->d_tile_v;
+  L.n_vtx = g->n_part;
+  L.e_cnt = g->e_part;
+  L.n_tiles = g->n_tiles;
+  L.d_head = g->d_head;
+  L.d_tail = g->d_tail;
+  L.d_carry = g->d_carry;
+  L.d_carry_flag = g->d_carry_flag;
+  L.d_block_agg = g->d_block_agg;
+  L.d_block_flag = g->d_block_flag;
+  L.n_fix_blocks = g->n_fix_blocks;
+  return L;
+}
+
 template <class Prog, class Shape>
 static int launch_pull_shape(luxb_graph* g, const PullArgs<Prog>& a) {
-  static int attr_ctas_dev[64];  // function attributes are per device: remember what each device was given
-  static int occ_dev[64];
-  static bool attr_init = false;
-  if (!attr_init) { for (int d = 0; d < 64; ++d) { attr_ctas_dev[d] = -1; occ_dev[d] = 0; } attr_init = true; }
-  int& attr_ctas = attr_ctas_dev[g->cfg.device & 63];
-  int& occ = occ_dev[g->cfg.device & 63];
   auto kern = pull_tile_kernel<Prog, Shape>;
-  int want = kDefaultPullCtas;
-  if (const char* env = getenv("LUXB_PULL_CTAS")) want = atoi(env);
-  if (want < 1) want = 1;
-  if (attr_ctas != want) {
-    // carve out exactly `want` CTAs' worth of shared memory; the rest of the 256 KB unified array stays L1
-    LUXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Shape::kSmemBytes));
-    int carve_pct = (int)std::min<size_t>(100, (want * (Shape::kSmemBytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
-    LUXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve_pct));
-    LUXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Shape::kThreads, Shape::kSmemBytes));
-    if (occ < 1) occ = 1;
-    if (occ > want) occ = want;
-    attr_ctas = want;
-  }
-  const uint32_t n_super = (g->n_tiles + Shape::kWarps - 1) / Shape::kWarps;
-  uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)g->num_sms * occ, n_super);
+  const int want = g->pull_ctas;
+  // carve out exactly `want` CTAs' worth of shared memory; the rest of the 256 KB unified array stays L1.
+  // (function attributes are per device and idempotent: set on every launch, no process-global cache)
+  LUXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Shape::kSmemBytes));
+  int carve_pct = (int)std::min<size_t>(100, (want * (Shape::kSmemBytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+  LUXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve_pct));
+  const uint32_t n_super = (a.n_tiles + Shape::kWarps - 1) / Shape::kWarps;
+  uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)g->num_sms * want, n_super);
   kern<<<grid, Shape::kThreads, Shape::kSmemBytes, g->stream>>>(a);
   LUXB_CUDA(cudaGetLastError());
   return 0;
 }
 
+static int kt_begin(luxb_graph* g) {
+  if (!g->kernel_timing) return 0;
+  if (g->kt_used + 2 > g->kt_events.size()) {
+    cudaEvent_t e0, e1;
+    LUXB_CUDA(cudaEventCreate(&e0));
+    LUXB_CUDA(cudaEventCreate(&e1));
+    g->kt_events.push_back(e0);
+    g->kt_events.push_back(e1);
+  }
+  LUXB_CUDA(cudaEventRecord(g->kt_events[g->kt_used], g->stream));
+  return 0;
+}
+static int kt_end(luxb_graph* g) {
+  if (!g->kernel_timing) return 0;
+  LUXB_CUDA(cudaEventRecord(g->kt_events[g->kt_used + 1], g->stream));
+  g->kt_used += 2;
+  return 0;
+}
+
 template <class Prog>
-static int launch_pull(luxb_graph* g, const typename Prog::Vertex* x_nat, const typename Prog::Vertex* x_hot, uint32_t hot_n,
-                       const uint32_t* src_idx, typename Prog::Vertex* out_local, const typename Prog::Params& prm,
-                       int out_replica /* -1: no peers */) {
-  if (g->n_tiles == 0) return 0;
+static void fill_fixup_args(PullArgs<Prog>& a, const PullLayout& L) {
+  a.tile_v = L.d_tile_v;
+  a.n_tiles = L.n_tiles;
+  a.head_partial = reinterpret_cast<typename Prog::Acc*>(L.d_head);
+  a.tail_partial = reinterpret_cast<typename Prog::Acc*>(L.d_tail);
+  a.carry = reinterpret_cast<typename Prog::Wide*>(L.d_carry);
+  a.carry_flag = L.d_carry_flag;
+  a.block_agg = reinterpret_cast<typename Prog::Wide*>(L.d_block_agg);
+  a.block_flag = L.d_block_flag;
+}
+
+template <class Prog>
+static int launch_fixup(luxb_graph* g, const PullArgs<Prog>& a, const PullLayout& L) {
+  if (L.n_tiles <= 1) return 0;
+  pull_fixup_scan_kernel<Prog><<<L.n_fix_blocks, kFixBlock, 0, g->stream>>>(a);
+  pull_fixup_blocks_kernel<Prog><<<1, 1024, 0, g->stream>>>(a, L.n_fix_blocks);
+  pull_fixup_apply_kernel<Prog><<<L.n_fix_blocks, kFixBlock, 0, g->stream>>>(a);
+  LUXB_CUDA(cudaGetLastError());
+  g->stats.kernel_launches += 3;
+  return 0;
+}
+
+// one pull sweep over layout L.  hub_bits != nullptr: those vertices get their raw sum (panel.cuh).
+template <class Prog>
+static int launch_pull(luxb_graph* g, const PullLayout& L, const typename Prog::Vertex* x_nat, const typename Prog::Vertex* x_hot,
+                       uint32_t hot_n, typename Prog::Vertex* out_local, const typename Prog::Params& prm,
+                       int out_replica /* -1: no peers */, const uint32_t* hub_bits = nullptr, bool timed = true) {
+  if (L.n_tiles == 0) return 0;
   PullArgs<Prog> a{};
-  a.row_end = g->d_row_end;
-  a.row_end32 = g->d_row_end32;
-  a.src = src_idx;
+  a.row_end = L.d_row_end;
+  a.row_end32 = L.d_row_end32;
+  a.src = reinterpret_cast<const uint32_t*>(L.d_src);
   a.x_nat = x_nat;
-  a.tile_v = g->d_tile_v;
-  a.n_part = g->n_part;
-  a.e_part = g->e_part;
-  a.n_tiles = g->n_tiles;
+  a.n_part = L.n_vtx;
+  a.e_part = L.e_cnt;
   a.row_left = g->row_left;
   a.x_old = x_nat;
   a.x_hot = x_hot;
   a.hot_n = hot_n;
   a.out = out_local;
-  a.head_partial = reinterpret_cast<typename Prog::Acc*>(g->d_head);
-  a.tail_partial = reinterpret_cast<typename Prog::Acc*>(g->d_tail);
-  a.carry = reinterpret_cast<typename Prog::Wide*>(g->d_carry);
-  a.carry_flag = g->d_carry_flag;
-  a.block_agg = reinterpret_cast<typename Prog::Wide*>(g->d_block_agg);
-  a.block_flag = g->d_block_flag;
+  fill_fixup_args(a, L);
   a.tile_counter = reinterpret_cast<uint32_t*>(g->d_counters + 2);
   LUXB_CUDA(cudaMemsetAsync(a.tile_counter, 0, 4, g->stream));
   a.prm = prm;
+  a.hub_bits = hub_bits;
+  a.raw_out = 0;
   a.n_peers = 0;
   if (out_replica >= 0 && g->p2p_ready && g->cfg.exchange == LUXB_EXCHANGE_P2P_FUSED) {
     for (int p = 0; p < g->P; ++p) {
@@ -934,43 +980,334 @@ static int launch_pull(luxb_graph* g, const typename Prog::Vertex* x_nat, const 
       a.peer_out[a.n_peers++] = reinterpret_cast<typename Prog::Vertex*>(g->peer_val[out_replica][p]) + g->row_left;
     }
   }
-  if (g->kernel_timing) {
-    if (g->kt_used + 2 > g->kt_events.size()) {
-      cudaEvent_t e0, e1;
-      LUXB_CUDA(cudaEventCreate(&e0));
-      LUXB_CUDA(cudaEventCreate(&e1));
-      g->kt_events.push_back(e0);
-      g->kt_events.push_back(e1);
-    }
-    LUXB_CUDA(cudaEventRecord(g->kt_events[g->kt_used], g->stream));
-  }
+  if (timed) LUXB_TRY(kt_begin(g));
   switch (g->pull_shape) {
 #define LUXB_CASE_SHAPE(id, ipt, warps, stages) \
     case id: LUXB_TRY((launch_pull_shape<Prog, PullShape##id>(g, a))); break;
     LUXB_PULL_SHAPES(LUXB_CASE_SHAPE)
     default: set_error("bad pull shape"); return LUXB_ERR_STATE;
   }
-  if (g->kernel_timing) {
-    LUXB_CUDA(cudaEventRecord(g->kt_events[g->kt_used + 1], g->stream));
-    g->kt_used += 2;
-  }
+  if (timed) LUXB_TRY(kt_end(g));
   g->stats.kernel_launches++;
   pt_mark(g, 0);
-  if (g->n_tiles > 1) {
-    pull_fixup_scan_kernel<Prog><<<g->n_fix_blocks, kFixBlock, 0, g->stream>>>(a);
-    pull_fixup_blocks_kernel<Prog><<<1, 1024, 0, g->stream>>>(a, g->n_fix_blocks);
-    pull_fixup_apply_kernel<Prog><<<g->n_fix_blocks, kFixBlock, 0, g->stream>>>(a);
-    LUXB_CUDA(cudaGetLastError());
-    g->stats.kernel_launches += 3;
-  }
+  LUXB_TRY(launch_fixup(g, a, L));
   pt_mark(g, 1);
   return 0;
 }
 }  // extern "C++"
 
+// ---- source-blocked PageRank sweep (panel.cuh) -----------------------------------------------------------------
+// shapes <items per lane, consumer warps, ring stages, shared-memory table capacity (values)>; one CTA per SM
+#define LUXB_PANEL_SHAPES(X) X(0, 7, 16, 2, 40960) X(1, 7, 8, 2, 49152) X(2, 9, 16, 2, 32768) X(3, 7, 24, 2, 32768) X(4, 5, 16, 2, 40960)
+#define LUXB_DECL_PSHAPE(id, ipt, warps, stages, tab) using PanelShape##id = PanelShape<ipt, warps, stages, tab>;
+LUXB_PANEL_SHAPES(LUXB_DECL_PSHAPE)
+struct PanelShapeInfo { int tile, super, tab; };
+#define LUXB_PSHAPE_INFO(id, ipt, warps, stages, tab) {PanelShape##id::kTile, PanelShape##id::kSuper, PanelShape##id::kTab},
+static const PanelShapeInfo kPanelShapeInfo[] = {LUXB_PANEL_SHAPES(LUXB_PSHAPE_INFO)};
+static const int kNumPanelShapes = sizeof(kPanelShapeInfo) / sizeof(PanelShapeInfo);
+
+extern "C++" {
+// temporaries of a build step: freed on every exit path
+struct DevTmp {
+  std::vector<void*> ptrs;
+  ~DevTmp() { for (void* q : ptrs) cudaFree(q); }
+  template <class T>
+  int alloc(T** out, uint64_t count) {
+    LUXB_TRY(dmalloc(out, count));
+    ptrs.push_back(*out);
+    return 0;
+  }
+  void release(void* q) {
+    for (size_t i = 0; i < ptrs.size(); ++i)
+      if (ptrs[i] == q) { cudaFree(q); ptrs.erase(ptrs.begin() + i); return; }
+  }
+  void keep(void* q) {  // ownership moves to the graph
+    for (size_t i = 0; i < ptrs.size(); ++i)
+      if (ptrs[i] == q) { ptrs.erase(ptrs.begin() + i); return; }
+  }
+};
+}  // extern "C++"
+
+static void free_layout(PullLayout& L) {
+  void* ptrs[] = {L.d_row_end, L.d_row_end32, L.d_src, L.d_tile_v, L.d_head, L.d_tail, L.d_carry, L.d_carry_flag, L.d_block_agg, L.d_block_flag};
+  for (void* q : ptrs) if (q) cudaFree(q);
+  L = PullLayout();
+}
+
+// tile table + fix-up scratch of a layout whose d_row_end (u64, n_vtx + 4 with sentinels) and d_src are in place
+static int finish_pull_layout(luxb_graph* g, PullLayout& L, uint32_t tile) {
+  const uint64_t total = (uint64_t)L.n_vtx + L.e_cnt;
+  const uint64_t nt = (total + tile - 1) / tile;
+  LUXB_ARG(nt < 0xFFFFFFFFull, "layout too large for the tile table");
+  L.n_tiles = (uint32_t)nt;
+  LUXB_TRY(dmalloc(&L.d_tile_v, (uint64_t)L.n_tiles + 2));
+  tile_table_kernel<<<grid_for((uint64_t)L.n_tiles + 1, 256, 1 << 20), 256, 0, g->stream>>>(L.d_row_end, L.n_vtx, L.e_cnt, tile,
+                                                                                           L.n_tiles, L.d_tile_v);
+  LUXB_CUDA(cudaGetLastError());
+  LUXB_TRY(dmalloc(&L.d_row_end32, (uint64_t)L.n_vtx + 8));
+  narrow_u64_to_u32_kernel<<<grid_for((uint64_t)L.n_vtx + 8, 256, 4096), 256, 0, g->stream>>>(L.d_row_end, (uint64_t)L.n_vtx + 4,
+                                                                                         L.d_row_end32, (uint64_t)L.n_vtx + 8);
+  LUXB_CUDA(cudaGetLastError());
+  LUXB_TRY(dmalloc((uint32_t**)&L.d_head, (uint64_t)L.n_tiles + 1));
+  LUXB_TRY(dmalloc((uint32_t**)&L.d_tail, (uint64_t)L.n_tiles + 1));
+  L.n_fix_blocks = (L.n_tiles + kFixBlock - 1) / kFixBlock;
+  LUXB_TRY(dmalloc((uint64_t**)&L.d_carry, (uint64_t)L.n_tiles + 1));
+  LUXB_TRY(dmalloc(&L.d_carry_flag, (uint64_t)L.n_tiles + 1));
+  LUXB_TRY(dmalloc((uint64_t**)&L.d_block_agg, (uint64_t)L.n_fix_blocks + 1));
+  LUXB_TRY(dmalloc(&L.d_block_flag, (uint64_t)L.n_fix_blocks + 1));
+  LUXB_CUDA(cudaStreamSynchronize(g->stream));
+  LUXB_CUDA(cudaFree(L.d_row_end));  // only the tile table needed the 64-bit offsets
+  L.d_row_end = nullptr;
+  return 0;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+// Split this partition's (hot-packed) CSC into the panel CSC (hot source block x hub destination) and the main CSC.
+// LUXB_SB = 0 off / 1 force / unset: automatic (on when the panel would take at least a fifth of a large partition).
+// Tuning: LUXB_SB_SHAPE, LUXB_SB_BS (values per block), LUXB_SB_BLOCKS (max blocks), LUXB_SB_MIN_INDEG (hub threshold).
+static int build_panel_layout(luxb_graph* g) {
+  g->sb_on = false;
+  const int mode = env_int("LUXB_SB", -1);
+  if (mode == 0 || g->hot_n == 0 || g->e_part == 0 || g->e_part >= 0xFFFFFFFFull || g->cfg.zero_copy_edges) return 0;
+  if (mode < 0 && g->e_part < (1ull << 24)) return 0;
+  g->sb_shape = env_int("LUXB_SB_SHAPE", 0);
+  if (g->sb_shape < 0 || g->sb_shape >= kNumPanelShapes) g->sb_shape = 0;
+  const PanelShapeInfo shp = kPanelShapeInfo[g->sb_shape];
+  uint32_t bs = (uint32_t)std::max(4, env_int("LUXB_SB_BS", shp.tab));
+  bs = std::min<uint32_t>(bs & ~3u, (uint32_t)shp.tab);
+  const uint32_t nb_max = (uint32_t)std::min(std::max(env_int("LUXB_SB_BLOCKS", 48), 1), kPanelMaxBlocks);
+  const uint32_t n_src = (uint32_t)std::min<uint64_t>(g->hot_n, (uint64_t)nb_max * bs);
+  const uint32_t NB = (n_src + bs - 1) / bs;
+  const uint32_t min_indeg = (uint32_t)std::max(env_int("LUXB_SB_MIN_INDEG", (int)(2 * NB)), 1);
+  const int grid = g->num_sms * 8;
+  DevTmp tmp;
+
+  // 1. hub destinations
+  uint32_t *d_flag = nullptr, *d_hub_idx = nullptr;
+  LUXB_TRY(tmp.alloc(&d_flag, (uint64_t)g->n_part + 1));
+  LUXB_TRY(tmp.alloc(&d_hub_idx, (uint64_t)g->n_part + 1));
+  hub_flag_kernel<<<grid, 256, 0, g->stream>>>(g->d_row_end, g->n_part, min_indeg, d_flag);
+  LUXB_CUDA(cudaGetLastError());
+  size_t tb = 0;
+  void* d_scan_tmp = nullptr;
+  LUXB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_flag, d_hub_idx, (int)g->n_part, g->stream));
+  LUXB_TRY(tmp.alloc((char**)&d_scan_tmp, tb + 256));
+  LUXB_CUDA(cub::DeviceScan::ExclusiveSum(d_scan_tmp, tb, d_flag, d_hub_idx, (int)g->n_part, g->stream));
+  uint32_t last_idx = 0, last_flag = 0;
+  LUXB_CUDA(cudaMemcpyAsync(&last_idx, d_hub_idx + g->n_part - 1, 4, cudaMemcpyDeviceToHost, g->stream));
+  LUXB_CUDA(cudaMemcpyAsync(&last_flag, d_flag + g->n_part - 1, 4, cudaMemcpyDeviceToHost, g->stream));
+  LUXB_CUDA(cudaStreamSynchronize(g->stream));
+  tmp.release(d_scan_tmp);
+  const uint32_t Nh = last_idx + last_flag;
+  if (Nh == 0) return 0;
+  uint32_t *d_hub_vtx = nullptr, *d_hub_bits = nullptr, *d_cov = nullptr;
+  LUXB_TRY(tmp.alloc(&d_hub_vtx, Nh));
+  LUXB_TRY(tmp.alloc(&d_hub_bits, ((uint64_t)g->n_part + 31) / 32 + 1));
+  LUXB_TRY(tmp.alloc(&d_cov, Nh));
+  hub_list_kernel<<<grid, 256, 0, g->stream>>>(d_flag, d_hub_idx, g->n_part, d_hub_vtx, d_hub_bits);
+  LUXB_CUDA(cudaGetLastError());
+
+  // 2. edge keys: block of the source for (hot source, hub destination) edges, 255 for the rest; 3. stable sort
+  uint8_t *d_key = nullptr, *d_key2 = nullptr;
+  uint64_t *d_pay = nullptr, *d_pay2 = nullptr;
+  LUXB_TRY(tmp.alloc(&d_key, g->e_part));
+  LUXB_TRY(tmp.alloc(&d_key2, g->e_part));
+  LUXB_TRY(tmp.alloc(&d_pay, g->e_part));
+  LUXB_TRY(tmp.alloc(&d_pay2, g->e_part));
+  edge_iota_kernel<<<grid, 256, 0, g->stream>>>(d_pay, d_key, g->e_part);
+  hub_key_kernel<<<grid, 256, 0, g->stream>>>(g->d_row_end, g->d_src_gather, d_hub_vtx, Nh, n_src, bs, d_key, d_pay, d_cov);
+  LUXB_CUDA(cudaGetLastError());
+  tb = 0;
+  LUXB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, d_key, d_key2, d_pay, d_pay2, (long long)g->e_part, 0, 8, g->stream));
+  LUXB_TRY(tmp.alloc((char**)&d_scan_tmp, tb + 256));
+  LUXB_CUDA(cub::DeviceRadixSort::SortPairs(d_scan_tmp, tb, d_key, d_key2, d_pay, d_pay2, (long long)g->e_part, 0, 8, g->stream));
+  unsigned long long* d_hist = nullptr;
+  LUXB_TRY(tmp.alloc(&d_hist, 256));
+  LUXB_CUDA(cudaMemsetAsync(d_hist, 0, 256 * 8, g->stream));
+  key_hist_kernel<<<grid, 256, 0, g->stream>>>(d_key2, g->e_part, d_hist);
+  LUXB_CUDA(cudaGetLastError());
+  unsigned long long hist[256];
+  LUXB_CUDA(cudaMemcpyAsync(hist, d_hist, sizeof(hist), cudaMemcpyDeviceToHost, g->stream));
+  LUXB_CUDA(cudaStreamSynchronize(g->stream));
+  tmp.release(d_scan_tmp);
+  tmp.release(d_key);
+  tmp.release(d_pay);
+  uint64_t e_cov = 0;
+  for (uint32_t b = 0; b < NB; ++b) e_cov += hist[b];
+  const uint64_t e_main = hist[255];
+  if (e_cov + e_main != g->e_part) { set_error("panel split lost edges (%llu + %llu != %llu)", (unsigned long long)e_cov,
+                                               (unsigned long long)e_main, (unsigned long long)g->e_part); return LUXB_ERR_STATE; }
+  if (e_cov == 0 || (mode < 0 && e_cov < g->e_part / 5)) return 0;
+
+  // 4. virtual-vertex bases: every block holds Nh (+ padding) virtual vertices, padded so that its merge items
+  //    (vertices + edges) are a whole number of super-tiles
+  uint64_t nv_virtual = 0, items = 0;
+  for (uint32_t b = 0; b < NB; ++b) {
+    const uint64_t it = (uint64_t)Nh + hist[b];
+    const uint64_t pad = (shp.super - it % shp.super) % shp.super;
+    g->sb_pb.vbase[b] = (uint32_t)nv_virtual;
+    nv_virtual += Nh + pad;
+    items += it + pad;
+    g->sb_super_end[b] = (uint32_t)(items / shp.super);
+    if (nv_virtual >= 0x7FFFFFF0ull || items / shp.super >= 0xFFFFFFF0ull) return 0;  // too many virtual vertices: keep the plain sweep
+  }
+  g->sb_pb.vbase[NB] = (uint32_t)nv_virtual;
+  const uint32_t NV = (uint32_t)nv_virtual;
+
+  // 5. panel CSC
+  PullLayout& PL = g->sb_panel;
+  PL = PullLayout();
+  PL.n_vtx = NV;
+  PL.e_cnt = e_cov;
+  uint16_t* d_src16 = nullptr;
+  uint32_t* d_vcount = nullptr;
+  LUXB_TRY(dmalloc(&d_src16, e_cov + 32));
+  PL.d_src = d_src16;
+  LUXB_CUDA(cudaMemsetAsync(d_src16, 0, (e_cov + 32) * 2, g->stream));
+  LUXB_TRY(tmp.alloc(&d_vcount, (uint64_t)NV + 1));
+  LUXB_CUDA(cudaMemsetAsync(d_vcount, 0, ((size_t)NV + 1) * 4, g->stream));
+  panel_fill_kernel<<<grid, 256, 0, g->stream>>>(d_key2, d_pay2, e_cov, g->d_src_gather, bs, g->sb_pb, d_src16, d_vcount);
+  LUXB_CUDA(cudaGetLastError());
+  LUXB_TRY(dmalloc(&PL.d_row_end, (uint64_t)NV + 4));
+  widen_u32_to_u64_kernel<<<grid, 256, 0, g->stream>>>(d_vcount, PL.d_row_end, NV);
+  tb = 0;
+  LUXB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, PL.d_row_end, PL.d_row_end, (int)NV, g->stream));
+  LUXB_TRY(tmp.alloc((char**)&d_scan_tmp, tb + 256));
+  LUXB_CUDA(cub::DeviceScan::InclusiveSum(d_scan_tmp, tb, PL.d_row_end, PL.d_row_end, (int)NV, g->stream));
+  pad_sentinels_kernel<<<1, 32, 0, g->stream>>>(PL.d_row_end, NV);
+  LUXB_CUDA(cudaGetLastError());
+  LUXB_CUDA(cudaStreamSynchronize(g->stream));
+  tmp.release(d_scan_tmp);
+  tmp.release(d_vcount);
+
+  // 6. main CSC: what is left, in the original (dst, src) order
+  PullLayout& ML = g->sb_main;
+  ML = PullLayout();
+  ML.n_vtx = g->n_part;
+  ML.e_cnt = e_main;
+  uint32_t* d_main_src = nullptr;
+  LUXB_TRY(dmalloc(&d_main_src, e_main + 8));
+  ML.d_src = d_main_src;
+  LUXB_CUDA(cudaMemsetAsync(d_main_src, 0, (e_main + 8) * 4, g->stream));
+  main_fill_kernel<<<grid, 256, 0, g->stream>>>(d_pay2 + e_cov, e_main, g->d_src_gather, d_main_src);
+  LUXB_TRY(dmalloc(&ML.d_row_end, (uint64_t)g->n_part + 4));
+  main_indeg_kernel<<<grid, 256, 0, g->stream>>>(g->d_row_end, g->n_part, d_flag, d_hub_idx, d_cov, ML.d_row_end);
+  LUXB_CUDA(cudaGetLastError());
+  tb = 0;
+  LUXB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, ML.d_row_end, ML.d_row_end, (int)g->n_part, g->stream));
+  LUXB_TRY(tmp.alloc((char**)&d_scan_tmp, tb + 256));
+  LUXB_CUDA(cub::DeviceScan::InclusiveSum(d_scan_tmp, tb, ML.d_row_end, ML.d_row_end, (int)g->n_part, g->stream));
+  pad_sentinels_kernel<<<1, 32, 0, g->stream>>>(ML.d_row_end, g->n_part);
+  uint64_t chk[2] = {0, 0};
+  LUXB_CUDA(cudaMemcpyAsync(&chk[0], ML.d_row_end + g->n_part - 1, 8, cudaMemcpyDeviceToHost, g->stream));
+  LUXB_CUDA(cudaMemcpyAsync(&chk[1], PL.d_row_end + NV - 1, 8, cudaMemcpyDeviceToHost, g->stream));
+  LUXB_CUDA(cudaStreamSynchronize(g->stream));
+  if (chk[0] != e_main || chk[1] != e_cov) { set_error("panel split: offsets do not add up"); return LUXB_ERR_STATE; }
+  tmp.release(d_scan_tmp);
+  tmp.release(d_key2);
+  tmp.release(d_pay2);
+
+  // 7. tile tables + fix-up scratch; 8. raw panel sums
+  LUXB_TRY(finish_pull_layout(g, PL, (uint32_t)shp.tile));
+  LUXB_TRY(finish_pull_layout(g, ML, (uint32_t)kPullTileOf[g->pull_shape]));
+  LUXB_TRY(dmalloc(&g->d_sb_partial, (uint64_t)NV + 1));
+  LUXB_CUDA(cudaMemsetAsync(g->d_sb_partial, 0, ((size_t)NV + 1) * 4, g->stream));
+  LUXB_CUDA(cudaStreamSynchronize(g->stream));
+  g->d_hub_vtx = d_hub_vtx; tmp.keep(d_hub_vtx);
+  g->d_hub_bits = d_hub_bits; tmp.keep(d_hub_bits);
+  g->sb_n_hub = Nh;
+  g->sb_n_blocks = NB;
+  g->sb_bs = bs;
+  g->sb_n_src = n_src;
+  g->sb_on = true;
+  g->stats.panel_edges = e_cov;
+  g->stats.panel_hubs = Nh;
+  g->stats.panel_blocks = NB;
+  if (g->cfg.verbose)
+    printf("[luxb rank %d] source-blocked sweep: %u hub destinations (in-degree >= %u) x %u blocks of %u hot sources; panel %llu edges "
+           "(%.1f %%) over %u virtual vertices, main %llu edges\n", g->cfg.rank, Nh, min_indeg, NB, bs, (unsigned long long)e_cov,
+           100.0 * e_cov / g->e_part, NV, (unsigned long long)e_main);
+  return 0;
+}
+
+extern "C++" {
+template <class Shape>
+static int launch_panel_shape(luxb_graph* g, const PanelArgs& a) {
+  auto kern = panel_tile_kernel<Shape>;
+  LUXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Shape::kSmemBytes));
+  LUXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  const uint32_t n_super = (a.n_tiles + Shape::kWarps - 1) / Shape::kWarps;
+  const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)g->num_sms, n_super);
+  kern<<<grid, Shape::kThreads, Shape::kSmemBytes, g->stream>>>(a);
+  LUXB_CUDA(cudaGetLastError());
+  return 0;
+}
+}  // extern "C++"
+
+// one PageRank sweep = panel sweep (shared-memory gathers) + main sweep (L1 gathers) + hub combine
+static int pagerank_sweep_blocked(luxb_graph* g, const float* x_old, float* x_new, const PageRankProgram::Params& prm, int out_replica) {
+  const PullLayout& PL = g->sb_panel;
+  PanelArgs pa{};
+  pa.row_end32 = PL.d_row_end32;
+  pa.src16 = reinterpret_cast<const uint16_t*>(PL.d_src);
+  pa.tile_v = PL.d_tile_v;
+  pa.n_vtx = PL.n_vtx;
+  pa.e_cnt = PL.e_cnt;
+  pa.n_tiles = PL.n_tiles;
+  pa.x_hot = (const float*)g->d_hot;
+  pa.bs = g->sb_bs;
+  pa.n_blocks = g->sb_n_blocks;
+  for (uint32_t b = 0; b < g->sb_n_blocks; ++b) pa.super_end[b] = g->sb_super_end[b];
+  pa.out = g->d_sb_partial;
+  pa.head_partial = (float*)PL.d_head;
+  pa.tail_partial = (float*)PL.d_tail;
+  pa.tile_counter = reinterpret_cast<uint32_t*>(g->d_counters + 4);
+  LUXB_CUDA(cudaMemsetAsync(pa.tile_counter, 0, 4, g->stream));
+  LUXB_TRY(kt_begin(g));
+  switch (g->sb_shape) {
+#define LUXB_CASE_PSHAPE(id, ipt, warps, stages, tab) \
+    case id: LUXB_TRY((launch_panel_shape<PanelShape##id>(g, pa))); break;
+    LUXB_PANEL_SHAPES(LUXB_CASE_PSHAPE)
+    default: set_error("bad panel shape"); return LUXB_ERR_STATE;
+  }
+  g->stats.kernel_launches++;
+  pt_mark(g, 5);
+  PullArgs<PageRankProgram> fa{};
+  fill_fixup_args(fa, PL);
+  fa.out = g->d_sb_partial;
+  fa.raw_out = 1;
+  fa.prm = prm;
+  LUXB_TRY(launch_fixup(g, fa, PL));
+  pt_mark(g, 1);
+  // main sweep; hub vertices keep their raw sums
+  LUXB_TRY(launch_pull<PageRankProgram>(g, g->sb_main, x_old, (const float*)g->d_hot, g->hot_n, x_new + g->row_left, prm, out_replica,
+                                        g->d_hub_bits, /*timed=*/false));
+  LUXB_TRY(kt_end(g));
+  CombineArgs<PageRankProgram> ca{};
+  ca.hub_vtx = g->d_hub_vtx;
+  ca.n_hub = g->sb_n_hub;
+  ca.n_blocks = g->sb_n_blocks;
+  ca.row_left = g->row_left;
+  ca.pb = g->sb_pb;
+  ca.partial = g->d_sb_partial;
+  ca.out = x_new + g->row_left;
+  ca.prm = prm;
+  ca.n_peers = 0;
+  if (out_replica >= 0 && g->p2p_ready && g->cfg.exchange == LUXB_EXCHANGE_P2P_FUSED)
+    for (int p = 0; p < g->P; ++p)
+      if (p != g->cfg.rank) ca.peer_out[ca.n_peers++] = reinterpret_cast<float*>(g->peer_val[out_replica][p]) + g->row_left;
+  combine_hub_kernel<PageRankProgram><<<grid_for(g->sb_n_hub, 256, g->num_sms * 8), 256, 0, g->stream>>>(ca);
+  LUXB_CUDA(cudaGetLastError());
+  g->stats.kernel_launches++;
+  pt_mark(g, 6);
+  return 0;
+}
+
 static int pagerank_iteration(luxb_graph* g) {
-  static int init = 0;
-  if (!init) { init = 1; const char* env = getenv("LUXB_PHASE_TIMING"); g_pt.on = env && atoi(env) != 0; }
   pt_mark(g, -1);
   PageRankProgram::Params prm;
   prm.init_rank = (1.0f - kAlpha) / (float)g->nv;  // pagerank_gpu.cu:144
@@ -979,8 +1316,12 @@ static int pagerank_iteration(luxb_graph* g) {
   float* x_new = (float*)g->d_val[1 - g->cur];
   const bool p2p = g->P > 1 && g->p2p_ready && g->cfg.exchange != LUXB_EXCHANGE_NCCL;
   const bool fused = p2p && g->cfg.exchange == LUXB_EXCHANGE_P2P_FUSED;
-  LUXB_TRY(launch_pull<PageRankProgram>(g, x_old, (const float*)g->d_hot, g->hot_n, g->hot_n ? g->d_src_gather : g->d_src,
-                                        x_new + g->row_left, prm, fused ? 1 - g->cur : -1));
+  if (g->sb_on) {
+    LUXB_TRY(pagerank_sweep_blocked(g, x_old, x_new, prm, fused ? 1 - g->cur : -1));
+  } else {
+    LUXB_TRY(launch_pull<PageRankProgram>(g, base_layout(g, g->hot_n ? g->d_src_gather : g->d_src), x_old, (const float*)g->d_hot,
+                                          g->hot_n, x_new + g->row_left, prm, fused ? 1 - g->cur : -1));
+  }
   const int me = g->cfg.rank;
   if (p2p && !fused) {
     // Balanced all-gather.  Edge-balanced partitions own very different numbers of vertices (RMAT-27 at P = 8:
@@ -1092,7 +1433,8 @@ static int label_iteration(luxb_graph* g) {
       hot_refresh_kernel<uint32_t><<<grid_for(g->hot_n, 256, g->num_sms * 8), 256, 0, g->stream>>>((uint32_t*)g->d_hot, lab, g->d_hot_order, 0, g->hot_n);
       g->stats.kernel_launches++;
     }
-    LUXB_TRY(launch_pull<Prog>(g, lab, (const uint32_t*)g->d_hot, g->hot_n, g->hot_n ? g->d_src_gather : g->d_src, g->d_cur, prm, -1));
+    LUXB_TRY(launch_pull<Prog>(g, base_layout(g, g->hot_n ? g->d_src_gather : g->d_src), lab, (const uint32_t*)g->d_hot, g->hot_n,
+                               g->d_cur, prm, -1));
     g->stats.edges_processed += g->e_part;
     g->stats.pull_iterations++;
   } else if (g->n_part && old_size) {
@@ -1448,11 +1790,10 @@ int luxb_get_local_csc(luxb_graph* g, luxb_eid* row_end_abs, luxb_vid* src, int3
 
 void luxb_close(luxb_graph* g) {
   if (!g) return;
-  if (g_pt.on && g_pt.cnt) {
-    fprintf(stderr, "[luxb rank %d] phase means over %ld iterations:", g->cfg.rank, g_pt.cnt);
-    for (int k = 0; k < 5; ++k) fprintf(stderr, " %s %.3f ms;", g_pt.name[k], g_pt.sum[k] / g_pt.cnt);
+  if (g->pt.on && g->pt.cnt) {
+    fprintf(stderr, "[luxb rank %d] phase means over %ld iterations:", g->cfg.rank, g->pt.cnt);
+    for (int k = 0; k < 7; ++k) fprintf(stderr, " %s %.3f ms;", kPhaseName[k], g->pt.sum[k] / g->pt.cnt);
     fprintf(stderr, "\n");
-    g_pt = PhaseTimer();
   }
   cudaSetDevice(g->cfg.device);
   if (g->stream) cudaStreamSynchronize(g->stream);
@@ -1475,6 +1816,11 @@ void luxb_close(luxb_graph* g) {
     if (std::find(g->host_allocs.begin(), g->host_allocs.end(), p) != g->host_allocs.end()) cudaFreeHost(p);
     else cudaFree(p);
   }
+  free_layout(g->sb_main);
+  free_layout(g->sb_panel);
+  if (g->d_hub_vtx) cudaFree(g->d_hub_vtx);
+  if (g->d_hub_bits) cudaFree(g->d_hub_bits);
+  if (g->d_sb_partial) cudaFree(g->d_sb_partial);
   if (g->h_hdr) cudaFreeHost(g->h_hdr);
   if (g->h_scratch) cudaFreeHost(g->h_scratch);
   for (cudaEvent_t e : g->kt_events) cudaEventDestroy(e);

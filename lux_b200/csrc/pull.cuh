@@ -69,9 +69,35 @@ struct PullArgs {
   uint32_t* block_flag;                // [nBlocks]
   uint32_t* tile_counter;              // dynamic super-tile scheduler (zeroed before every launch)
   typename Prog::Params prm;
+  // source-blocked sweep (panel.cuh): vertices whose bit is set in hub_bits get their RAW sum stored (no update(), no
+  // peer stores) — combine_hub_kernel finishes them; raw_out != 0 does that for every vertex (the panel CSC's fix-up)
+  const uint32_t* hub_bits;
+  int raw_out;
   int n_peers;                                        // P2P exchange: peers' slice pointers (local index)
   typename Prog::Vertex* peer_out[LUXB_MAX_PEERS];
 };
+
+template <class Prog>
+__device__ __forceinline__ bool store_raw(const PullArgs<Prog>& a, uint32_t v) {
+  if (a.raw_out) return true;
+  return a.hub_bits != nullptr && ((__ldg(a.hub_bits + (v >> 5)) >> (v & 31)) & 1u);
+}
+
+template <class Prog>
+__device__ __forceinline__ void store_vertex(const PullArgs<Prog>& a, uint32_t v, typename Prog::Acc sum) {
+  using Vertex = typename Prog::Vertex;
+  if (store_raw(a, v)) {
+    Vertex r;
+    static_assert(sizeof(Vertex) == sizeof(typename Prog::Acc), "raw sums travel in the value slot");
+    memcpy(&r, &sum, sizeof(r));
+    a.out[v] = r;
+    return;
+  }
+  Vertex oldv = Prog::kNeedsOld ? __ldg(a.x_nat + a.row_left + v) : Vertex();
+  Vertex nv_ = Prog::update(a.row_left + v, sum, oldv, a.prm);
+  a.out[v] = nv_;
+  for (int p = 0; p < a.n_peers; ++p) a.peer_out[p][v] = nv_;
+}
 
 __global__ void tile_table_kernel(const uint64_t* __restrict__ row_end, uint32_t n_part, uint64_t e_part, uint32_t tile,
                                   uint32_t n_tiles, uint32_t* __restrict__ tile_v) {
@@ -275,11 +301,7 @@ __global__ void __launch_bounds__(Shape::kThreads) pull_tile_kernel(const __grid
       // ---- update() + coalesced stores (own replica and, in P2P mode, every peer's replica) ----
       for (uint32_t li = lane; li < n_v; li += 32) {
         if (li == 0 && t != 0) continue;  // may continue from previous tiles: finished by the fix-up kernels
-        uint32_t v = i0 + li;
-        Vertex oldv = Prog::kNeedsOld ? __ldg(a.x_nat + a.row_left + v) : Vertex();
-        Vertex nv_ = Prog::update(a.row_left + v, sums[li], oldv, a.prm);
-        a.out[v] = nv_;
-        for (int p = 0; p < a.n_peers; ++p) a.peer_out[p][v] = nv_;
+        store_vertex<Prog>(a, i0 + li, sums[li]);
       }
       __syncwarp();  // sums[] reads done before the next tile's walk writes it
     } else {
@@ -411,11 +433,7 @@ __global__ void __launch_bounds__(kFixBlock) pull_fixup_apply_kernel(const __gri
   Wide c = a.carry[t];
   if (!a.carry_flag[t]) c = Prog::wcombine(a.block_agg[blockIdx.x], c);
   Wide totalw = Prog::wcombine(c, Prog::widen(a.head_partial[t]));
-  const uint32_t v = i0;
-  typename Prog::Vertex oldv = Prog::kNeedsOld ? a.x_nat[a.row_left + v] : typename Prog::Vertex();
-  typename Prog::Vertex nv_ = Prog::update(a.row_left + v, Prog::narrow(totalw), oldv, a.prm);
-  a.out[v] = nv_;
-  for (int p = 0; p < a.n_peers; ++p) a.peer_out[p][v] = nv_;
+  store_vertex<Prog>(a, i0, Prog::narrow(totalw));
 }
 
 }  // namespace luxb

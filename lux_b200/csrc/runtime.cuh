@@ -4,6 +4,34 @@
 #include <vector>
 #include "comm.h"
 #include "common.cuh"
+#include "panel.cuh"
+
+// one CSC swept by a merge-path tile kernel, with its tile table and fix-up scratch
+struct PullLayout {
+  uint64_t* d_row_end = nullptr;    // [n_vtx + 4] (may be released once the tile table exists)
+  uint32_t* d_row_end32 = nullptr;  // [n_vtx + 8]
+  void* d_src = nullptr;            // u32 gather ids (main) or u16 block-local offsets (panel)
+  uint32_t* d_tile_v = nullptr;
+  uint32_t n_vtx = 0;
+  uint64_t e_cnt = 0;
+  uint32_t n_tiles = 0;
+  void* d_head = nullptr;
+  void* d_tail = nullptr;
+  void* d_carry = nullptr;
+  uint32_t* d_carry_flag = nullptr;
+  void* d_block_agg = nullptr;
+  uint32_t* d_block_flag = nullptr;
+  uint32_t n_fix_blocks = 0;
+};
+
+// dev aid: LUXB_PHASE_TIMING=1 prints the mean device time of each phase of a PageRank iteration at luxb_close
+struct PhaseTimer {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> tag;
+  double sum[8] = {0};
+  long cnt = 0;
+};
 
 struct luxb_graph {
   luxb_config cfg{};
@@ -82,6 +110,21 @@ struct luxb_graph {
   void* peer_hot[LUXB_MAX_PARTS]{};
   uint32_t* d_sync = nullptr;
   uint64_t ag_chunk = 0, hot_chunk = 0;  // equal chunk sizes (elements) of the balanced all-gather
+
+  // source-blocked PageRank sweep (panel.cuh): hub destinations x hot source blocks in shared memory
+  bool sb_on = false;
+  PullLayout sb_main, sb_panel;
+  uint32_t sb_n_hub = 0, sb_n_blocks = 0, sb_bs = 0, sb_n_src = 0;
+  int sb_shape = 0;
+  uint32_t* d_hub_vtx = nullptr;
+  uint32_t* d_hub_bits = nullptr;
+  float* d_sb_partial = nullptr;   // [NV] raw panel sums
+  luxb::PanelBases sb_pb{};
+  uint32_t sb_super_end[luxb::kPanelMaxBlocks]{};
+
+  // launch configuration resolved once at open time (no getenv / function-static state on the hot path)
+  int pull_ctas = 3;
+  PhaseTimer pt;
 
   // optional per-launch timing of the dominant kernel
   bool kernel_timing = false;
