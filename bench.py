@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--scale", type=int, default=27, help="RMAT scale (27 = BASELINE config; smaller only for debugging)")
     ap.add_argument("--edge-factor", type=int, default=16)
     ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "p2p", "p2p_fused"],
-                    help="auto = fused P2P stores up to 4 GPUs, balanced all-gather (re-chunk + ncclAllGather) beyond (measured best)")
+                    help="auto = p2p: packed balanced all-gather (pack + NVLink re-chunk + ncclAllGather of equal chunks)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
@@ -235,7 +235,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if args.exchange == "auto":
-        args.exchange = "p2p_fused" if world <= 4 else "p2p"
+        args.exchange = "p2p"
     exchange = {"p2p": L.EXCHANGE_P2P, "p2p_fused": L.EXCHANGE_P2P_FUSED, "nccl": L.EXCHANGE_NCCL}[args.exchange]
     t_build0 = time.perf_counter()
     g = L.LuxGraph.from_rmat(scale, nv, ne, SEED, rank=rank, nranks=world, device=local, exchange=exchange)
@@ -287,39 +287,47 @@ def main():
     edges_total = ne * ITERS_PER_STEP * args.steps
     value = edges_total / dev_s_max / 1e6
 
-    # ---- end to end through the C ABI with host buffers (pinned): H2D initial values + iterations + D2H result ----
+    # ---- end to end through the C ABI with host buffers (pinned): every rank moves ITS partition's values over PCIe
+    # (luxb_set_local_values: H2D of the slice + device-side exchange; luxb_get_local_values: D2H of the slice), like
+    # the per-GPU tasks of the reference touch only their own region.  Together the ranks move nv values each way. ----
     e2e = None
     if not args.no_e2e:
-        x_host = torch.empty(nv, dtype=torch.float32).pin_memory()
-        y_host = torch.empty(nv, dtype=torch.float32).pin_memory()
-        x_np, y_np = x_host.numpy(), y_host.numpy()
-        g.values(out=x_np)
+        x_host = torch.empty(max(n_part, 1), dtype=torch.float32).pin_memory()
+        y_host = torch.empty(max(n_part, 1), dtype=torch.float32).pin_memory()
+        x_np, y_np = x_host.numpy()[:n_part], y_host.numpy()[:n_part]
+        g.local_values(out=x_np)
         barrier()
         for _ in range(1):
-            g.set_values(x_np); g.iterate(ITERS_PER_STEP); g.values(out=y_np)
+            g.set_local_values(x_np); g.iterate(ITERS_PER_STEP); g.local_values(out=y_np)
         barrier()
         e0 = time.perf_counter()
         for _ in range(args.steps):
-            g.set_values(x_np)
+            g.set_local_values(x_np)
             g.iterate(ITERS_PER_STEP)
-            g.values(out=y_np)
+            g.local_values(out=y_np)
         barrier()
         e1 = time.perf_counter()
         te = torch.tensor([e1 - e0], dtype=torch.float64, device="cuda")
         if dist is not None:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": edges_total / float(te[0]) / 1e6, "unit": "MTEPS", "h2d_bytes_per_step": 4 * nv * world,
-               "d2h_bytes_per_step": 4 * nv * world, "ms_per_step": 1e3 * float(te[0]) / args.steps,
-               "what": "luxb_set_values(pinned host x0) + luxb_iterate(%d) + luxb_get_values(pinned host) per step, "
-                       "graph structure resident (the reference's timed region also excludes load/init, pagerank.cc:108-116)"
-                       % ITERS_PER_STEP}
+        e2e = {"value": edges_total / float(te[0]) / 1e6, "unit": "MTEPS", "h2d_bytes_per_step": 4 * nv,
+               "d2h_bytes_per_step": 4 * nv, "ms_per_step": 1e3 * float(te[0]) / args.steps,
+               "what": "per rank: luxb_set_local_values(pinned host slice) + luxb_iterate(%d) + luxb_get_local_values(pinned host "
+                       "slice) per step; bytes are summed over the ranks; graph structure resident (the reference's timed region "
+                       "also excludes load/init, pagerank.cc:108-116)" % ITERS_PER_STEP}
 
-    # ---- roofline of the dominant kernel (this rank's partition) ----
+    # ---- roofline of the dominant kernel(s) (this rank's partition): one "launch" = one whole-partition sweep ----
+    st_now = g.stats()
+    if st_now["panel_edges"]:
+        sweep_kernel = ("seg_tile_kernel<panel: %d hubs x %d hot-source blocks in shared memory, %.1f%% of the edges> + panel fix-up + "
+                        "seg_tile_kernel<main, L1 gathers>" % (st_now["panel_hubs"], st_now["panel_blocks"], 100.0 * st_now["panel_edges"] / max(e_part, 1)))
+    else:
+        sweep_kernel = "seg_tile_kernel<main, L1 gathers>"
     peak, peak_src = load_peaks()
     algo_bytes = 8 * e_part + 16 * n_part  # 4 B src id + 4 B gathered value per edge; 8+4+4 per vertex
     achieved = algo_bytes / max(kern_avg_max, 1e-12) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "pull_tile_kernel<PageRankProgram>", "avg_launch_ms": 1e3 * kern_avg_max,
+                "traffic": None, "kernel": sweep_kernel, "avg_launch_ms": 1e3 * kern_avg_max,
                 "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
                 "note": "traffic: see profiles/ (ncu dram__bytes_read.sum + dram__bytes_write.sum)"}
     prof = os.path.join(ROOT, "profiles", "latest_traffic.json")
@@ -361,9 +369,9 @@ def main():
     # the exchange is covered.  The same sample feeds the CPU baseline at N = 1. ----
     parity, cpu_base = None, None
     if not args.no_parity:
-        x_k = g.values() if rank == 0 else None
+        x_k = g.values()   # collective on several ranks: completes the natural-order replica (exchanged packed otherwise)
         g.iterate(1)
-        x_k1 = g.values() if rank == 0 else None
+        x_k1 = g.values()
         if rank == 0:
             import oracle as O
             b = g.bounds()

@@ -121,6 +121,10 @@ int luxb_p2p_import(luxb_graph* g, const void* all_blobs, size_t blob_bytes_each
 /* Forget imported peer mappings: the P2P exchanges silently degrade to the NCCL exchange.  Call on EVERY rank when the
  * import failed on any of them (all ranks must use the same exchange). */
 int luxb_p2p_disable(luxb_graph* g);
+/* Unmap the peers' buffers from this process (the exchanges fall back to NCCL).  Teardown order on several ranks: every
+ * rank calls luxb_p2p_disconnect, the ranks synchronise (any barrier), then each calls luxb_close — CUDA forbids freeing
+ * an exported buffer while an importer still has it mapped. */
+int luxb_p2p_disconnect(luxb_graph* g);
 
 /* ---- Pull/PushInitTask (+PullScanTask): app state ------------------------------------------------------- */
 /* = pull_scan_task_impl (pull_model.inl:322-345) + pull_init_task_impl (pagerank_gpu.cu:182-281,
@@ -137,10 +141,18 @@ int luxb_iterate(luxb_graph* g, int iters, uint64_t* active_out);
 int luxb_run_to_convergence(luxb_graph* g, int max_iters, int* iters_out);
 
 /* ---- results / check / stats -------------------------------------------------------------------------------- */
-/* Full vertex-value array (what the reference holds in dist_lr[iter%2]): nv * {4 | 4 | 80} bytes. */
+/* Full vertex-value array (what the reference holds in dist_lr[iter%2]): nv * {4 | 4 | 80} bytes.  PageRank on
+ * nranks > 1 exchanges only the values that are ever gathered each iteration and completes the full array on demand:
+ * there the call is collective (every rank calls it at the same point). */
 int luxb_get_values(luxb_graph* g, void* host_out, size_t bytes);
 /* Overwrite the vertex values (H2D), e.g. to restart from a checkpoint; push apps: all vertices become active. */
 int luxb_set_values(luxb_graph* g, const void* host_in, size_t bytes);
+/* The same for THIS RANK'S partition only: (row_right - row_left + 1) values in local order — what a per-GPU task of
+ * the reference touches (its own region, e.g. pull_init_task_impl writes new_pr[rowLeft..rowRight], pagerank_gpu.cu:
+ * 255-259).  set: H2D of the slice, then the ranks exchange on the device exactly as after an iteration; get: D2H of the
+ * slice.  nranks host buffers together move nv values over PCIe instead of nranks * nv.  Collective on nranks > 1. */
+int luxb_set_local_values(luxb_graph* g, const void* host_in, size_t bytes);
+int luxb_get_local_values(luxb_graph* g, void* host_out, size_t bytes);
 /* CheckTask / check_kernel invariants (components_gpu.cu:768-837, sssp_gpu.cu:773-843): number of violating
  * edges over this rank's partition; PageRank / col_filter have no check in the reference -> LUXB_ERR_ARG. */
 int luxb_check(luxb_graph* g, uint64_t* mistakes_out);

@@ -208,8 +208,9 @@ class LuxGraph:
         flag = torch.tensor([ok], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if int(flag) == 0:
-            L.luxb_p2p_disable(self._h)
+            L.luxb_p2p_disconnect(self._h)
             return False
+        self._p2p = True
         return True
 
     # ---- phases -------------------------------------------------------------------------------------------
@@ -238,6 +239,24 @@ class LuxGraph:
     def set_values(self, arr):
         arr = np.ascontiguousarray(arr, _VDTYPE[self.app])
         _chk(load_library().luxb_set_values(self._h, _p(arr), C.c_size_t(arr.nbytes)), "luxb_set_values")
+
+    def local_range(self):
+        v = self.device_view()
+        return v.row_left, (v.row_right - v.row_left + 1) & 0xFFFFFFFF
+
+    def local_values(self, out=None):
+        """This rank's partition only (local order): D2H of (row_right - row_left + 1) values."""
+        _, n = self.local_range()
+        shape = (n, CF_K) if self.app == APP_COLFILTER else (n,)
+        if out is None:
+            out = np.empty(shape, _VDTYPE[self.app])
+        _chk(load_library().luxb_get_local_values(self._h, _p(out), C.c_size_t(out.nbytes)), "luxb_get_local_values")
+        return out
+
+    def set_local_values(self, arr):
+        """H2D of this rank's partition, then the device-side exchange (collective on nranks > 1)."""
+        arr = np.ascontiguousarray(arr, _VDTYPE[self.app])
+        _chk(load_library().luxb_set_local_values(self._h, _p(arr), C.c_size_t(arr.nbytes)), "luxb_set_local_values")
 
     def check(self):
         bad = C.c_uint64(0)
@@ -285,6 +304,16 @@ class LuxGraph:
 
     def close(self):
         if self._h:
+            if getattr(self, "_p2p", False):
+                # exported buffers may only be freed once every importer has unmapped them
+                load_library().luxb_p2p_disconnect(self._h)
+                try:
+                    import torch.distributed as dist
+                    if dist.is_initialized():
+                        dist.barrier()
+                except Exception:  # noqa: BLE001
+                    pass
+                self._p2p = False
             load_library().luxb_close(self._h)
             self._h = None
 

@@ -13,6 +13,7 @@
 #include "cf.cuh"
 #include "pull.cuh"
 #include "panel.cuh"
+#include "seg.cuh"
 #include "push.cuh"
 #include "runtime.cuh"
 
@@ -501,9 +502,9 @@ int luxb_comm_init(luxb_graph* g, const char id[LUXB_UNIQUE_ID_BYTES]) {
 }
 
 struct P2PBlob {
-  cudaIpcMemHandle_t val[2];
-  cudaIpcMemHandle_t hot;
-  int has_hot;
+  cudaIpcMemHandle_t val[2];  // natural-order replicas (col_filter stores into its peers' replicas)
+  cudaIpcMemHandle_t xt[2];   // PageRank: packed transfer arrays
+  int has_val, has_xt;
 };
 
 int luxb_p2p_export(luxb_graph* g, void* blob, size_t* blob_bytes) {
@@ -514,9 +515,15 @@ int luxb_p2p_export(luxb_graph* g, void* blob, size_t* blob_bytes) {
   P2PBlob b;
   memset(&b, 0, sizeof(b));
   LUXB_CUDA(cudaSetDevice(g->cfg.device));
-  for (int k = 0; k < 2; ++k)
-    if (g->d_val[k]) LUXB_CUDA(cudaIpcGetMemHandle(&b.val[k], g->d_val[k]));
-  if (g->d_hot) { LUXB_CUDA(cudaIpcGetMemHandle(&b.hot, g->d_hot)); b.has_hot = 1; }
+  if (g->cfg.app == LUXB_COLFILTER) {
+    for (int k = 0; k < 2; ++k)
+      if (g->d_val[k]) LUXB_CUDA(cudaIpcGetMemHandle(&b.val[k], g->d_val[k]));
+    b.has_val = 1;
+  }
+  if (g->packed) {
+    for (int k = 0; k < 2; ++k) LUXB_CUDA(cudaIpcGetMemHandle(&b.xt[k], g->d_xt[k]));
+    b.has_xt = 1;
+  }
   memcpy(blob, &b, sizeof(b));
   *blob_bytes = sizeof(P2PBlob);
   return 0;
@@ -530,12 +537,30 @@ int luxb_p2p_import(luxb_graph* g, const void* all_blobs, size_t blob_bytes_each
   LUXB_ARG(g->comm != nullptr, "P2P exchange still needs the communicator for its iteration barrier");
   LUXB_CUDA(cudaSetDevice(g->cfg.device));
   const P2PBlob* blobs = reinterpret_cast<const P2PBlob*>(all_blobs);
+  auto undo = [&]() {  // an import that fails half-way leaves nothing mapped
+    for (int p = 0; p < g->P; ++p) {
+      if (p == g->cfg.rank) continue;
+      for (int k = 0; k < 2; ++k) {
+        if (g->peer_val[k][p]) { cudaIpcCloseMemHandle(g->peer_val[k][p]); g->peer_val[k][p] = nullptr; }
+        if (g->peer_xt[k][p]) { cudaIpcCloseMemHandle(g->peer_xt[k][p]); g->peer_xt[k][p] = nullptr; }
+      }
+    }
+  };
   for (int p = 0; p < g->P; ++p) {
-    if (p == g->cfg.rank) { g->peer_val[0][p] = g->d_val[0]; g->peer_val[1][p] = g->d_val[1]; g->peer_hot[p] = g->d_hot; continue; }
-    if (blobs[p].has_hot) LUXB_CUDA(cudaIpcOpenMemHandle(&g->peer_hot[p], blobs[p].hot, cudaIpcMemLazyEnablePeerAccess));
+    if (p == g->cfg.rank) {
+      for (int k = 0; k < 2; ++k) { g->peer_val[k][p] = g->d_val[k]; g->peer_xt[k][p] = g->d_xt[k]; }
+      continue;
+    }
     for (int k = 0; k < 2; ++k) {
-      if (!g->d_val[k]) continue;
-      LUXB_CUDA(cudaIpcOpenMemHandle(&g->peer_val[k][p], blobs[p].val[k], cudaIpcMemLazyEnablePeerAccess));
+      cudaError_t e = cudaSuccess;
+      if (blobs[p].has_val && g->d_val[k]) e = cudaIpcOpenMemHandle(&g->peer_val[k][p], blobs[p].val[k], cudaIpcMemLazyEnablePeerAccess);
+      if (e == cudaSuccess && blobs[p].has_xt && g->d_xt[k])
+        e = cudaIpcOpenMemHandle(&g->peer_xt[k][p], blobs[p].xt[k], cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        set_error("cudaIpcOpenMemHandle (rank %d's buffers): %s", p, cudaGetErrorString(e));
+        undo();
+        return LUXB_ERR_CUDA;
+      }
     }
   }
   g->p2p_ready = true;
@@ -548,7 +573,48 @@ int luxb_p2p_disable(luxb_graph* g) {
   return 0;
 }
 
+// close every peer buffer mapped into this process
+static void p2p_unmap(luxb_graph* g) {
+  for (int p = 0; p < g->P; ++p) {
+    if (p == g->cfg.rank) continue;
+    for (int k = 0; k < 2; ++k) {
+      if (g->peer_val[k][p]) { cudaIpcCloseMemHandle(g->peer_val[k][p]); g->peer_val[k][p] = nullptr; }
+      if (g->peer_xt[k][p]) { cudaIpcCloseMemHandle(g->peer_xt[k][p]); g->peer_xt[k][p] = nullptr; }
+    }
+  }
+  g->p2p_ready = false;
+}
+
+int luxb_p2p_disconnect(luxb_graph* g) {
+  LUXB_ARG(g != nullptr, "graph is NULL");
+  LUXB_CUDA(cudaSetDevice(g->cfg.device));
+  if (g->stream) LUXB_CUDA(cudaStreamSynchronize(g->stream));
+  p2p_unmap(g);
+  return 0;
+}
+
 // ---- init ---------------------------------------------------------------------------------------------------
+extern "C++" {
+// temporaries of a build step: freed on every exit path
+struct DevTmp {
+  std::vector<void*> ptrs;
+  ~DevTmp() { for (void* q : ptrs) cudaFree(q); }
+  template <class T>
+  int alloc(T** out, uint64_t count) {
+    LUXB_TRY(dmalloc(out, count));
+    ptrs.push_back(*out);
+    return 0;
+  }
+  void release(void* q) {
+    for (size_t i = 0; i < ptrs.size(); ++i)
+      if (ptrs[i] == q) { cudaFree(q); ptrs.erase(ptrs.begin() + i); return; }
+  }
+  void keep(void* q) {  // ownership moves to the graph
+    for (size_t i = 0; i < ptrs.size(); ++i)
+      if (ptrs[i] == q) { ptrs.erase(ptrs.begin() + i); return; }
+  }
+};
+}  // extern "C++"
 static int build_push_csr(luxb_graph* g) {
   // CSR-by-source over this partition's own edges (init_push_* kernels, components_gpu.cu:550-607):
   // stable radix sort of (src, dst) pairs by src keeps each source's destinations ascending -> deterministic.
@@ -661,9 +727,12 @@ static int set_l2_persisting_window(luxb_graph* g, void* base, size_t bytes) {
 }
 
 // Choose the hot set (largest out-degrees, at most LUXB_HOT_MB megabytes of values, default 64 MB ~ half of L2) and
-// rewrite this partition's source ids as indices into Z = [hot copy | natural] (see build.cuh).
-static int build_hot_layout(luxb_graph* g) {
+// rewrite this partition's source ids as indices into the gather space Z = [hot copies in global hotness order | cold]
+// (see build.cuh).  cold = the natural-order value array, or — compact_cold, the packed exchange of PageRank on several
+// ranks — only the cold vertices that are ever gathered, in id order.
+static int build_hot_layout(luxb_graph* g, bool compact_cold) {
   g->hot_n = 0;
+  g->packed = false;
   double hot_mb = 64.0;
   if (const char* env = getenv("LUXB_HOT_MB")) hot_mb = atof(env);
   uint64_t h_max = (uint64_t)(hot_mb * 1e6 / 4.0);
@@ -671,14 +740,14 @@ static int build_hot_layout(luxb_graph* g) {
   if (h_max > g->nv) h_max = g->nv;
   const int grid = g->num_sms * 8;
   const uint32_t cap = 4096;
+  DevTmp tmp;
   unsigned long long* d_hist = nullptr;
-  LUXB_TRY(dmalloc(&d_hist, cap + 1));
+  LUXB_TRY(tmp.alloc(&d_hist, cap + 1));
   LUXB_CUDA(cudaMemsetAsync(d_hist, 0, (cap + 1) * 8, g->stream));
   degree_hist_kernel<<<grid, 256, 0, g->stream>>>(g->d_deg, g->nv, cap, d_hist);
   std::vector<unsigned long long> hist(cap + 1);
   LUXB_CUDA(cudaMemcpyAsync(hist.data(), d_hist, (cap + 1) * 8, cudaMemcpyDeviceToHost, g->stream));
   LUXB_CUDA(cudaStreamSynchronize(g->stream));
-  LUXB_CUDA(cudaFree(d_hist));
   // smallest tau >= 2 with |{deg >= tau}| <= h_max  (degree-1 vertices are gathered once: packing cannot help them)
   uint64_t above = 0;
   uint32_t tau = cap + 1;
@@ -692,12 +761,12 @@ static int build_hot_layout(luxb_graph* g) {
   uint64_t *d_keys = nullptr, *d_keys2 = nullptr;
   uint32_t *d_ids = nullptr, *d_ids2 = nullptr, *d_map = nullptr;
   unsigned int* d_cursor = nullptr;  // [0] cursor, [1 .. P] per-owner counts
-  LUXB_TRY(dmalloc(&d_keys, H));
-  LUXB_TRY(dmalloc(&d_keys2, H));
-  LUXB_TRY(dmalloc(&d_ids, H));
-  LUXB_TRY(dmalloc(&d_ids2, H));
+  LUXB_TRY(tmp.alloc(&d_keys, H));
+  LUXB_TRY(tmp.alloc(&d_keys2, H));
+  LUXB_TRY(tmp.alloc(&d_ids, H));
+  LUXB_TRY(tmp.alloc(&d_ids2, H));
   LUXB_TRY(dmalloc(&g->d_hot_order, H));
-  LUXB_TRY(dmalloc(&d_cursor, 1 + LUXB_MAX_PARTS));
+  LUXB_TRY(tmp.alloc(&d_cursor, 1 + LUXB_MAX_PARTS));
   LUXB_CUDA(cudaMemsetAsync(d_cursor, 0, 4 * (1 + LUXB_MAX_PARTS), g->stream));
   PartTable pt{};
   pt.P = g->P;
@@ -710,40 +779,79 @@ static int build_hot_layout(luxb_graph* g) {
   int vbits = 1;
   while ((1ull << vbits) < (uint64_t)g->nv) ++vbits;
   LUXB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, d_ids, d_ids2, d_keys, d_keys2, (int)H, 0, vbits, g->stream));
-  LUXB_CUDA(cudaMalloc(&d_tmp, tb + 256));
+  LUXB_TRY(tmp.alloc((char**)&d_tmp, tb + 256));
   LUXB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb, d_ids, d_ids2, d_keys, d_keys2, (int)H, 0, vbits, g->stream));
   LUXB_CUDA(cudaStreamSynchronize(g->stream));
-  LUXB_CUDA(cudaFree(d_tmp));
+  tmp.release(d_tmp);
   tb = 0;
-  LUXB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, d_keys2, d_keys, d_ids2, g->d_hot_order, (int)H, 0, 40, g->stream));
-  LUXB_CUDA(cudaMalloc(&d_tmp, tb + 256));
-  LUXB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb, d_keys2, d_keys, d_ids2, g->d_hot_order, (int)H, 0, 40, g->stream));
+  LUXB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, d_keys2, d_keys, d_ids2, g->d_hot_order, (int)H, 0, 32, g->stream));
+  LUXB_TRY(tmp.alloc((char**)&d_tmp, tb + 256));
+  LUXB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb, d_keys2, d_keys, d_ids2, g->d_hot_order, (int)H, 0, 32, g->stream));
   unsigned int h_cnt[1 + LUXB_MAX_PARTS];
   LUXB_CUDA(cudaMemcpyAsync(h_cnt, d_cursor, sizeof(h_cnt), cudaMemcpyDeviceToHost, g->stream));
   LUXB_CUDA(cudaStreamSynchronize(g->stream));
+  tmp.release(d_tmp);
   g->hot_off[0] = 0;
   for (int p = 0; p < g->P; ++p) g->hot_off[p + 1] = g->hot_off[p] + h_cnt[1 + p];
-  LUXB_TRY(dmalloc(&d_map, g->nv));
-  gather_map_init_kernel<<<grid, 256, 0, g->stream>>>(d_map, g->nv, H);
+  LUXB_TRY(tmp.alloc(&d_map, g->nv));
+  if (compact_cold && g->P > 1) {
+    // cold-active vertices (0 < deg < tau), ranked in id order; owner p's share is [cold_off[p], cold_off[p+1])
+    uint32_t *d_cflag = nullptr, *d_crank = nullptr, *d_okeys = nullptr, *d_okeys2 = nullptr, *d_ranks = nullptr;
+    LUXB_TRY(tmp.alloc(&d_cflag, (uint64_t)g->nv + 1));
+    LUXB_TRY(tmp.alloc(&d_crank, (uint64_t)g->nv + 1));
+    cold_flag_kernel<<<grid, 256, 0, g->stream>>>(g->d_deg, g->nv, tau, d_cflag);
+    LUXB_CUDA(cudaMemsetAsync(d_cflag + g->nv, 0, 4, g->stream));
+    tb = 0;
+    LUXB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_cflag, d_crank, (int)g->nv + 1, g->stream));
+    LUXB_TRY(tmp.alloc((char**)&d_tmp, tb + 256));
+    LUXB_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_cflag, d_crank, (int)g->nv + 1, g->stream));
+    for (int p = 0; p <= g->P; ++p) {
+      const uint32_t at = p < g->P ? std::min(g->rl[p], g->nv) : g->nv;  // empty partitions sit at nv
+      LUXB_CUDA(cudaMemcpyAsync(&g->cold_off[p], d_crank + at, 4, cudaMemcpyDeviceToHost, g->stream));
+    }
+    LUXB_CUDA(cudaStreamSynchronize(g->stream));
+    tmp.release(d_tmp);
+    g->cold_n = g->cold_off[g->P];
+    gather_map_compact_kernel<<<grid, 256, 0, g->stream>>>(d_map, d_crank, g->nv, H);
+    // transfer order of the hot values: grouped by owner (stable: hotness order inside a group)
+    LUXB_TRY(tmp.alloc(&d_okeys, H));
+    LUXB_TRY(tmp.alloc(&d_okeys2, H));
+    LUXB_TRY(tmp.alloc(&d_ranks, H));
+    LUXB_TRY(dmalloc(&g->d_zperm, H));
+    owner_keys_kernel<<<grid, 256, 0, g->stream>>>(g->d_hot_order, H, pt, d_okeys, d_ranks);
+    LUXB_CUDA(cudaGetLastError());
+    tb = 0;
+    LUXB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, d_okeys, d_okeys2, d_ranks, g->d_zperm, (int)H, 0, 8, g->stream));
+    LUXB_TRY(tmp.alloc((char**)&d_tmp, tb + 256));
+    LUXB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb, d_okeys, d_okeys2, d_ranks, g->d_zperm, (int)H, 0, 8, g->stream));
+    const int me = g->cfg.rank;
+    const uint32_t nh_me = g->hot_off[me + 1] - g->hot_off[me], nc_me = g->cold_off[me + 1] - g->cold_off[me];
+    LUXB_TRY(dmalloc(&g->d_pack_list, (uint64_t)nh_me + nc_me + 1));
+    if (nh_me)
+      pack_list_hot_kernel<<<grid_for(nh_me, 256, grid), 256, 0, g->stream>>>(g->d_hot_order, g->d_zperm, g->hot_off[me], nh_me, g->row_left,
+                                                                              g->d_pack_list);
+    if (g->n_part)
+      pack_list_cold_kernel<<<grid, 256, 0, g->stream>>>(d_cflag, d_crank, g->row_left, g->n_part, g->cold_off[me], g->d_pack_list + nh_me);
+    LUXB_CUDA(cudaGetLastError());
+    LUXB_CUDA(cudaStreamSynchronize(g->stream));
+    tmp.release(d_tmp);
+    g->packed = true;
+  } else {
+    gather_map_init_kernel<<<grid, 256, 0, g->stream>>>(d_map, g->nv, H);
+  }
   gather_map_hot_kernel<<<grid, 256, 0, g->stream>>>(d_map, g->d_hot_order, H);
   LUXB_TRY(edge_alloc(g, &g->d_src_gather, g->e_part + 8));
   LUXB_CUDA(cudaMemsetAsync(g->d_src_gather, 0, (g->e_part + 8) * 4, g->stream));
   remap_src_kernel<<<grid, 256, 0, g->stream>>>(g->d_src, g->e_part, d_map, g->d_src_gather);
   LUXB_CUDA(cudaGetLastError());
   LUXB_CUDA(cudaStreamSynchronize(g->stream));
-  LUXB_CUDA(cudaFree(d_tmp));
-  LUXB_CUDA(cudaFree(d_keys));
-  LUXB_CUDA(cudaFree(d_keys2));
-  LUXB_CUDA(cudaFree(d_ids));
-  LUXB_CUDA(cudaFree(d_ids2));
-  LUXB_CUDA(cudaFree(d_cursor));
-  LUXB_CUDA(cudaFree(d_map));
   g->hot_n = H;
   return 0;
 }
 
 static int allgather_slices(luxb_graph* g, void* replica, size_t elem_bytes);
-static int build_panel_layout(luxb_graph* g);
+static int build_pagerank_sweep(luxb_graph* g);
+static int pagerank_publish(luxb_graph* g, float* x_new);
 
 int luxb_init(luxb_graph* g) {
   LUXB_ARG(g != nullptr, "graph is NULL");
@@ -759,22 +867,28 @@ int luxb_init(luxb_graph* g) {
       hist_src_kernel<<<grid, 256, 0, g->stream>>>(g->d_src, g->e_part, g->d_deg);  // pull_scan_task_impl
       LUXB_CUDA(cudaGetLastError());
       if (g->P > 1) LUXB_NCCL(nccl().AllReduce(g->d_deg, g->d_deg, g->nv, ncclUint32, ncclSum, g->comm, g->stream));
-      LUXB_TRY(build_hot_layout(g));
-      LUXB_TRY(build_panel_layout(g));
-      g->ag_chunk = ((uint64_t)g->nv + g->P - 1) / g->P;  // equal chunks of the balanced all-gather
-      g->ag_chunk = (g->ag_chunk + 31) & ~31ull;
-      for (int k = 0; k < 2; ++k) LUXB_TRY(dmalloc((float**)&g->d_val[k], g->ag_chunk * g->P));
+      LUXB_TRY(build_hot_layout(g, /*compact_cold=*/true));
+      LUXB_TRY(build_pagerank_sweep(g));
+      for (int k = 0; k < 2; ++k) LUXB_TRY(dmalloc((float**)&g->d_val[k], (uint64_t)g->nv + 64));
       pr_init_kernel<<<grid, 256, 0, g->stream>>>(g->d_deg, g->nv, (float*)g->d_val[0]);
       LUXB_CUDA(cudaMemsetAsync(g->d_val[1], 0, (size_t)g->nv * 4, g->stream));
       if (g->hot_n) {
-        g->hot_chunk = (((uint64_t)g->hot_n + g->P - 1) / g->P + 31) & ~31ull;
         // + one whole table of slack: the panel kernel always bulk-loads full blocks (panel.cuh)
-        LUXB_TRY(dmalloc((float**)&g->d_hot, g->hot_chunk * g->P + 65536));
-        LUXB_CUDA(cudaMemsetAsync(g->d_hot, 0, (g->hot_chunk * g->P + 65536) * 4, g->stream));
-        hot_refresh_kernel<float><<<grid_for(g->hot_n, 256, grid), 256, 0, g->stream>>>((float*)g->d_hot, (const float*)g->d_val[0], g->d_hot_order, 0, g->hot_n);
+        LUXB_TRY(dmalloc((float**)&g->d_hot, (uint64_t)g->hot_n + 65536));
+        LUXB_CUDA(cudaMemsetAsync(g->d_hot, 0, ((size_t)g->hot_n + 65536) * 4, g->stream));
         LUXB_TRY(set_l2_persisting_window(g, g->d_hot, (size_t)g->hot_n * 4));
       }
+      if (g->packed) {
+        g->xt_chunk = ((((uint64_t)g->hot_n + g->cold_n + g->P - 1) / g->P) + 31) & ~31ull;
+        for (int k = 0; k < 2; ++k) {
+          LUXB_TRY(dmalloc(&g->d_xt[k], g->xt_chunk * g->P));
+          LUXB_CUDA(cudaMemsetAsync(g->d_xt[k], 0, g->xt_chunk * g->P * 4, g->stream));
+        }
+      }
       LUXB_CUDA(cudaGetLastError());
+      // every rank holds the complete x0: publish it (packs this rank's share, exchanges, fills the hot copies)
+      LUXB_TRY(pagerank_publish(g, (float*)g->d_val[0]));
+      g->replica_stale = false;
       break;
     }
     case LUXB_COLFILTER: {
@@ -816,7 +930,7 @@ int luxb_init(luxb_graph* g) {
         hist_src_kernel<<<grid, 256, 0, g->stream>>>(g->d_src, g->e_part, g->d_deg);
         LUXB_CUDA(cudaGetLastError());
         if (g->P > 1) LUXB_NCCL(nccl().AllReduce(g->d_deg, g->d_deg, g->nv, ncclUint32, ncclSum, g->comm, g->stream));
-        LUXB_TRY(build_hot_layout(g));
+        LUXB_TRY(build_hot_layout(g, /*compact_cold=*/false));
         if (g->hot_n) {
           LUXB_TRY(dmalloc((uint32_t**)&g->d_hot, g->hot_n));
           LUXB_TRY(set_l2_persisting_window(g, g->d_hot, (size_t)g->hot_n * 4));
@@ -951,9 +1065,9 @@ static int launch_fixup(luxb_graph* g, const PullArgs<Prog>& a, const PullLayout
 
 // one pull sweep over layout L.  hub_bits != nullptr: those vertices get their raw sum (panel.cuh).
 template <class Prog>
-static int launch_pull(luxb_graph* g, const PullLayout& L, const typename Prog::Vertex* x_nat, const typename Prog::Vertex* x_hot,
-                       uint32_t hot_n, typename Prog::Vertex* out_local, const typename Prog::Params& prm,
-                       int out_replica /* -1: no peers */, const uint32_t* hub_bits = nullptr, bool timed = true) {
+static int launch_pull(luxb_graph* g, const PullLayout& L, const typename Prog::Vertex* x_nat, const typename Prog::Vertex* x_cold,
+                       const typename Prog::Vertex* x_hot, uint32_t hot_n, typename Prog::Vertex* out_local,
+                       const typename Prog::Params& prm, const uint32_t* hub_bits = nullptr, bool timed = true) {
   if (L.n_tiles == 0) return 0;
   PullArgs<Prog> a{};
   a.row_end = L.d_row_end;
@@ -963,7 +1077,7 @@ static int launch_pull(luxb_graph* g, const PullLayout& L, const typename Prog::
   a.n_part = L.n_vtx;
   a.e_part = L.e_cnt;
   a.row_left = g->row_left;
-  a.x_old = x_nat;
+  a.x_old = x_cold;  // gather ids >= hot_n index this array at (id - hot_n)
   a.x_hot = x_hot;
   a.hot_n = hot_n;
   a.out = out_local;
@@ -974,12 +1088,6 @@ static int launch_pull(luxb_graph* g, const PullLayout& L, const typename Prog::
   a.hub_bits = hub_bits;
   a.raw_out = 0;
   a.n_peers = 0;
-  if (out_replica >= 0 && g->p2p_ready && g->cfg.exchange == LUXB_EXCHANGE_P2P_FUSED) {
-    for (int p = 0; p < g->P; ++p) {
-      if (p == g->cfg.rank) continue;
-      a.peer_out[a.n_peers++] = reinterpret_cast<typename Prog::Vertex*>(g->peer_val[out_replica][p]) + g->row_left;
-    }
-  }
   if (timed) LUXB_TRY(kt_begin(g));
   switch (g->pull_shape) {
 #define LUXB_CASE_SHAPE(id, ipt, warps, stages) \
@@ -996,69 +1104,28 @@ static int launch_pull(luxb_graph* g, const PullLayout& L, const typename Prog::
 }
 }  // extern "C++"
 
-// ---- source-blocked PageRank sweep (panel.cuh) -----------------------------------------------------------------
-// shapes <items per lane, consumer warps, ring stages, shared-memory table capacity (values)>; one CTA per SM
-#define LUXB_PANEL_SHAPES(X) X(0, 7, 16, 2, 40960) X(1, 7, 8, 2, 49152) X(2, 9, 16, 2, 32768) X(3, 7, 24, 2, 32768) X(4, 5, 16, 2, 40960)
-#define LUXB_DECL_PSHAPE(id, ipt, warps, stages, tab) using PanelShape##id = PanelShape<ipt, warps, stages, tab>;
-LUXB_PANEL_SHAPES(LUXB_DECL_PSHAPE)
-struct PanelShapeInfo { int tile, super, tab; };
-#define LUXB_PSHAPE_INFO(id, ipt, warps, stages, tab) {PanelShape##id::kTile, PanelShape##id::kSuper, PanelShape##id::kTab},
-static const PanelShapeInfo kPanelShapeInfo[] = {LUXB_PANEL_SHAPES(LUXB_PSHAPE_INFO)};
-static const int kNumPanelShapes = sizeof(kPanelShapeInfo) / sizeof(PanelShapeInfo);
-
-extern "C++" {
-// temporaries of a build step: freed on every exit path
-struct DevTmp {
-  std::vector<void*> ptrs;
-  ~DevTmp() { for (void* q : ptrs) cudaFree(q); }
-  template <class T>
-  int alloc(T** out, uint64_t count) {
-    LUXB_TRY(dmalloc(out, count));
-    ptrs.push_back(*out);
-    return 0;
-  }
-  void release(void* q) {
-    for (size_t i = 0; i < ptrs.size(); ++i)
-      if (ptrs[i] == q) { cudaFree(q); ptrs.erase(ptrs.begin() + i); return; }
-  }
-  void keep(void* q) {  // ownership moves to the graph
-    for (size_t i = 0; i < ptrs.size(); ++i)
-      if (ptrs[i] == q) { ptrs.erase(ptrs.begin() + i); return; }
-  }
-};
-}  // extern "C++"
+// ---- flagged segmented-scan sweep (seg.cuh) and its source-blocked variant (panel.cuh) ------------------------------
+// shapes <consumer warps, ring stages, rounds of 256 edges per warp piece>
+#define LUXB_SEG_MAIN_SHAPES(X) X(0, 8, 2, 2) X(1, 8, 3, 1) X(2, 12, 2, 1) X(3, 8, 2, 4) X(4, 16, 2, 1) X(5, 8, 4, 1)
+#define LUXB_DECL_MSHAPE(id, warps, stages, rounds) using SegMain##id = SegShape<warps, stages, rounds, false, 0>;
+LUXB_SEG_MAIN_SHAPES(LUXB_DECL_MSHAPE)
+// panel shapes: + shared-memory table capacity (values, <= 32768: 15-bit offsets); one CTA per SM
+#define LUXB_SEG_PANEL_SHAPES(X) X(0, 16, 2, 4, 32768) X(1, 24, 2, 2, 32768) X(2, 31, 2, 2, 32768) X(3, 16, 2, 2, 32768) X(4, 24, 2, 4, 24576) X(5, 31, 2, 1, 32768)
+#define LUXB_DECL_PSHAPE(id, warps, stages, rounds, tab) using SegPanel##id = SegShape<warps, stages, rounds, true, tab>;
+LUXB_SEG_PANEL_SHAPES(LUXB_DECL_PSHAPE)
+struct SegShapeInfo { int piece, stage_edges, tab; };
+#define LUXB_MSHAPE_INFO(id, warps, stages, rounds) {SegMain##id::kPiece, SegMain##id::kStageEdges, 0},
+#define LUXB_PSHAPE_INFO(id, warps, stages, rounds, tab) {SegPanel##id::kPiece, SegPanel##id::kStageEdges, SegPanel##id::kTab},
+static const SegShapeInfo kSegMainInfo[] = {LUXB_SEG_MAIN_SHAPES(LUXB_MSHAPE_INFO)};
+static const SegShapeInfo kSegPanelInfo[] = {LUXB_SEG_PANEL_SHAPES(LUXB_PSHAPE_INFO)};
+static const int kNumSegMain = sizeof(kSegMainInfo) / sizeof(SegShapeInfo);
+static const int kNumSegPanel = sizeof(kSegPanelInfo) / sizeof(SegShapeInfo);
 
 static void free_layout(PullLayout& L) {
-  void* ptrs[] = {L.d_row_end, L.d_row_end32, L.d_src, L.d_tile_v, L.d_head, L.d_tail, L.d_carry, L.d_carry_flag, L.d_block_agg, L.d_block_flag};
+  void* ptrs[] = {L.d_row_end, L.d_row_end32, L.d_src, L.d_tile_v, L.d_head, L.d_tail, L.d_carry, L.d_carry_flag, L.d_block_agg, L.d_block_flag,
+                  L.d_close, L.d_empty};
   for (void* q : ptrs) if (q) cudaFree(q);
   L = PullLayout();
-}
-
-// tile table + fix-up scratch of a layout whose d_row_end (u64, n_vtx + 4 with sentinels) and d_src are in place
-static int finish_pull_layout(luxb_graph* g, PullLayout& L, uint32_t tile) {
-  const uint64_t total = (uint64_t)L.n_vtx + L.e_cnt;
-  const uint64_t nt = (total + tile - 1) / tile;
-  LUXB_ARG(nt < 0xFFFFFFFFull, "layout too large for the tile table");
-  L.n_tiles = (uint32_t)nt;
-  LUXB_TRY(dmalloc(&L.d_tile_v, (uint64_t)L.n_tiles + 2));
-  tile_table_kernel<<<grid_for((uint64_t)L.n_tiles + 1, 256, 1 << 20), 256, 0, g->stream>>>(L.d_row_end, L.n_vtx, L.e_cnt, tile,
-                                                                                           L.n_tiles, L.d_tile_v);
-  LUXB_CUDA(cudaGetLastError());
-  LUXB_TRY(dmalloc(&L.d_row_end32, (uint64_t)L.n_vtx + 8));
-  narrow_u64_to_u32_kernel<<<grid_for((uint64_t)L.n_vtx + 8, 256, 4096), 256, 0, g->stream>>>(L.d_row_end, (uint64_t)L.n_vtx + 4,
-                                                                                         L.d_row_end32, (uint64_t)L.n_vtx + 8);
-  LUXB_CUDA(cudaGetLastError());
-  LUXB_TRY(dmalloc((uint32_t**)&L.d_head, (uint64_t)L.n_tiles + 1));
-  LUXB_TRY(dmalloc((uint32_t**)&L.d_tail, (uint64_t)L.n_tiles + 1));
-  L.n_fix_blocks = (L.n_tiles + kFixBlock - 1) / kFixBlock;
-  LUXB_TRY(dmalloc((uint64_t**)&L.d_carry, (uint64_t)L.n_tiles + 1));
-  LUXB_TRY(dmalloc(&L.d_carry_flag, (uint64_t)L.n_tiles + 1));
-  LUXB_TRY(dmalloc((uint64_t**)&L.d_block_agg, (uint64_t)L.n_fix_blocks + 1));
-  LUXB_TRY(dmalloc(&L.d_block_flag, (uint64_t)L.n_fix_blocks + 1));
-  LUXB_CUDA(cudaStreamSynchronize(g->stream));
-  LUXB_CUDA(cudaFree(L.d_row_end));  // only the tile table needed the 64-bit offsets
-  L.d_row_end = nullptr;
-  return 0;
 }
 
 static int env_int(const char* name, int dflt) {
@@ -1066,23 +1133,132 @@ static int env_int(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
-// Split this partition's (hot-packed) CSC into the panel CSC (hot source block x hub destination) and the main CSC.
+extern "C++" {
+// Build the flagged stream of a CSC (seg.cuh).  row_end: inclusive end offsets (u64) of n_vtx "vertices" whose edges,
+// in CSC order, carry the gather ids `ids`; blk: the vertex / edge ranges of the blocks (one block = plain stream;
+// wbase / hshift are filled here).  Every block is padded with 1 .. stage_edges head-flagged dummy words to a whole
+// number of stages.  On return L holds words, close list, tile_v (heads before each piece), fix-up scratch and, if
+// want_empty, the list of vertices without edges.  super_end (optional) receives the first stage after each block.
+template <class Word, class In>
+static int build_seg_stream(luxb_graph* g, PullLayout& L, const uint64_t* d_row_end, uint32_t n_vtx, const In* d_ids, uint64_t e_cnt,
+                            StreamBlocks& blk, uint32_t stage_edges, uint32_t piece, uint32_t vtx_offset, bool want_empty,
+                            uint32_t* super_end) {
+  const int grid = g->num_sms * 8;
+  DevTmp tmp;
+  L = PullLayout();
+  L.n_vtx = n_vtx;
+  L.e_cnt = e_cnt;
+  uint64_t words = 0, pads_total = 0;
+  for (uint32_t b = 0; b < blk.n_blocks; ++b) {
+    const uint64_t eb = blk.ebase[b + 1] - blk.ebase[b];
+    const uint64_t pad = stage_edges - eb % stage_edges;  // 1 .. stage_edges: the first pad closes the block's last vertex
+    blk.wbase[b] = words;
+    blk.hshift[b] = pads_total;
+    words += eb + pad;
+    pads_total += pad;
+    if (super_end) super_end[b] = (uint32_t)(words / stage_edges);
+  }
+  blk.wbase[blk.n_blocks] = words;
+  blk.hshift[blk.n_blocks] = pads_total;
+  LUXB_ARG(words / piece < 0xFFFFFFF0ull && words / stage_edges < 0xFFFFFFF0ull, "stream too large");
+  L.n_words = words;
+  L.n_stages = (uint32_t)(words / stage_edges);
+  L.n_tiles = (uint32_t)(words / piece);
+  // 1. non-empty vertices and their rank
+  uint32_t *d_flag = nullptr, *d_rank = nullptr;
+  LUXB_TRY(tmp.alloc(&d_flag, (uint64_t)n_vtx + 1));
+  LUXB_TRY(tmp.alloc(&d_rank, (uint64_t)n_vtx + 1));
+  nonempty_flag_kernel<<<grid, 256, 0, g->stream>>>(d_row_end, n_vtx, d_flag);
+  LUXB_CUDA(cudaMemsetAsync(d_flag + n_vtx, 0, 4, g->stream));
+  size_t tb = 0;
+  void* d_tmp = nullptr;
+  LUXB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_flag, d_rank, (int)n_vtx + 1, g->stream));
+  LUXB_TRY(tmp.alloc((char**)&d_tmp, tb + 256));
+  LUXB_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_flag, d_rank, (int)n_vtx + 1, g->stream));
+  uint32_t n_seg = 0;
+  LUXB_CUDA(cudaMemcpyAsync(&n_seg, d_rank + n_vtx, 4, cudaMemcpyDeviceToHost, g->stream));
+  LUXB_CUDA(cudaStreamSynchronize(g->stream));
+  tmp.release(d_tmp);
+  // 2. words: ids, then pads, then head flags; close list (entry j + 1 = owner of head j, dummies for the pads)
+  Word* d_words = nullptr;
+  LUXB_TRY(dmalloc(&d_words, words + 64));
+  L.d_src = d_words;
+  if (e_cnt) stream_copy_kernel<Word, In><<<grid, 256, 0, g->stream>>>(d_ids, e_cnt, blk, d_words);
+  for (uint32_t b = 0; b < blk.n_blocks; ++b) {
+    const uint64_t from = blk.wbase[b] + (blk.ebase[b + 1] - blk.ebase[b]);
+    stream_pad_kernel<Word><<<grid_for(blk.wbase[b + 1] - from, 256, grid), 256, 0, g->stream>>>(d_words, from, blk.wbase[b + 1]);
+  }
+  LUXB_CUDA(cudaGetLastError());
+  const uint64_t n_heads = (uint64_t)n_seg + pads_total;
+  LUXB_ARG(n_heads < 0xFFFFFFF0ull, "too many segments");
+  LUXB_TRY(dmalloc(&L.d_close, n_heads + 2));
+  LUXB_CUDA(cudaMemsetAsync(L.d_close, 0xFF, (n_heads + 2) * 4, g->stream));
+  stream_heads_kernel<Word><<<grid, 256, 0, g->stream>>>(d_row_end, n_vtx, d_flag, d_rank, blk, d_words, L.d_close, vtx_offset);
+  LUXB_CUDA(cudaGetLastError());
+  // 3. heads before each piece
+  uint32_t* d_cnt = nullptr;
+  LUXB_TRY(tmp.alloc(&d_cnt, (uint64_t)L.n_tiles + 2));
+  LUXB_CUDA(cudaMemsetAsync(d_cnt, 0, ((size_t)L.n_tiles + 2) * 4, g->stream));
+  piece_heads_kernel<Word><<<grid, 256, 0, g->stream>>>(d_words, L.n_tiles, piece, d_cnt);
+  LUXB_CUDA(cudaGetLastError());
+  LUXB_TRY(dmalloc(&L.d_tile_v, (uint64_t)L.n_tiles + 2));
+  tb = 0;
+  LUXB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_cnt, L.d_tile_v, (int)L.n_tiles + 1, g->stream));
+  LUXB_TRY(tmp.alloc((char**)&d_tmp, tb + 256));
+  LUXB_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_cnt, L.d_tile_v, (int)L.n_tiles + 1, g->stream));
+  uint32_t heads_counted = 0;
+  LUXB_CUDA(cudaMemcpyAsync(&heads_counted, L.d_tile_v + L.n_tiles, 4, cudaMemcpyDeviceToHost, g->stream));
+  // 4. vertices without edges
+  if (want_empty) {
+    L.n_empty = n_vtx - n_seg;
+    LUXB_TRY(dmalloc(&L.d_empty, (uint64_t)L.n_empty + 1));
+    empty_list_kernel<<<grid, 256, 0, g->stream>>>(d_flag, d_rank, n_vtx, L.d_empty);
+    LUXB_CUDA(cudaGetLastError());
+  }
+  LUXB_CUDA(cudaStreamSynchronize(g->stream));
+  if ((uint64_t)heads_counted != n_heads) {
+    set_error("flagged stream: %u heads counted, %llu expected", heads_counted, (unsigned long long)n_heads);
+    return LUXB_ERR_STATE;
+  }
+  // 5. fix-up scratch
+  LUXB_TRY(dmalloc((uint32_t**)&L.d_head, (uint64_t)L.n_tiles + 1));
+  LUXB_TRY(dmalloc((uint32_t**)&L.d_tail, (uint64_t)L.n_tiles + 1));
+  L.n_fix_blocks = (L.n_tiles + kFixBlock - 1) / kFixBlock;
+  LUXB_TRY(dmalloc((uint64_t**)&L.d_carry, (uint64_t)L.n_tiles + 1));
+  LUXB_TRY(dmalloc(&L.d_carry_flag, (uint64_t)L.n_tiles + 1));
+  LUXB_TRY(dmalloc((uint64_t**)&L.d_block_agg, (uint64_t)L.n_fix_blocks + 1));
+  LUXB_TRY(dmalloc(&L.d_block_flag, (uint64_t)L.n_fix_blocks + 1));
+  return 0;
+}
+}  // extern "C++"
+
+// the whole partition as one flagged stream (PageRank without the source-blocked split)
+static int build_plain_seg_layout(luxb_graph* g) {
+  const SegShapeInfo shp = kSegMainInfo[g->seg_main_shape];
+  StreamBlocks blk{};
+  blk.n_blocks = 1;
+  blk.vfirst[0] = 0; blk.vfirst[1] = g->n_part;
+  blk.ebase[0] = 0; blk.ebase[1] = g->e_part;
+  return build_seg_stream<uint32_t, uint32_t>(g, g->sb_main, g->d_row_end, g->n_part, g->hot_n ? g->d_src_gather : g->d_src, g->e_part, blk,
+                                              (uint32_t)shp.stage_edges, (uint32_t)shp.piece, 0, true, nullptr);
+}
+
+// Split this partition's (hot-packed) CSC into the panel (hot source block x hub destination, 15-bit offsets, gathered
+// from shared memory) and the main stream (everything else, gathered through L1).
 // LUXB_SB = 0 off / 1 force / unset: automatic (on when the panel would take at least a fifth of a large partition).
-// Tuning: LUXB_SB_SHAPE, LUXB_SB_BS (values per block), LUXB_SB_BLOCKS (max blocks), LUXB_SB_MIN_INDEG (hub threshold).
+// Tuning: LUXB_SB_BS (values per block), LUXB_SB_BLOCKS (max blocks), LUXB_SB_MIN_INDEG (hub threshold).
 static int build_panel_layout(luxb_graph* g) {
   g->sb_on = false;
   const int mode = env_int("LUXB_SB", -1);
   if (mode == 0 || g->hot_n == 0 || g->e_part == 0 || g->e_part >= 0xFFFFFFFFull || g->cfg.zero_copy_edges) return 0;
   if (mode < 0 && g->e_part < (1ull << 24)) return 0;
-  g->sb_shape = env_int("LUXB_SB_SHAPE", 0);
-  if (g->sb_shape < 0 || g->sb_shape >= kNumPanelShapes) g->sb_shape = 0;
-  const PanelShapeInfo shp = kPanelShapeInfo[g->sb_shape];
+  const SegShapeInfo shp = kSegPanelInfo[g->seg_panel_shape];
   uint32_t bs = (uint32_t)std::max(4, env_int("LUXB_SB_BS", shp.tab));
   bs = std::min<uint32_t>(bs & ~3u, (uint32_t)shp.tab);
   const uint32_t nb_max = (uint32_t)std::min(std::max(env_int("LUXB_SB_BLOCKS", 48), 1), kPanelMaxBlocks);
   const uint32_t n_src = (uint32_t)std::min<uint64_t>(g->hot_n, (uint64_t)nb_max * bs);
   const uint32_t NB = (n_src + bs - 1) / bs;
-  const uint32_t min_indeg = (uint32_t)std::max(env_int("LUXB_SB_MIN_INDEG", (int)(2 * NB)), 1);
+  const uint32_t min_indeg = (uint32_t)std::max(env_int("LUXB_SB_MIN_INDEG", 64), 1);
   const int grid = g->num_sms * 8;
   DevTmp tmp;
 
@@ -1103,7 +1279,7 @@ static int build_panel_layout(luxb_graph* g) {
   LUXB_CUDA(cudaStreamSynchronize(g->stream));
   tmp.release(d_scan_tmp);
   const uint32_t Nh = last_idx + last_flag;
-  if (Nh == 0) return 0;
+  if (Nh == 0 || (uint64_t)Nh * NB >= 0x7FFFFFF0ull) return 0;
   uint32_t *d_hub_vtx = nullptr, *d_hub_bits = nullptr, *d_cov = nullptr;
   LUXB_TRY(tmp.alloc(&d_hub_vtx, Nh));
   LUXB_TRY(tmp.alloc(&d_hub_bits, ((uint64_t)g->n_part + 31) / 32 + 1));
@@ -1143,77 +1319,68 @@ static int build_panel_layout(luxb_graph* g) {
                                                (unsigned long long)e_main, (unsigned long long)g->e_part); return LUXB_ERR_STATE; }
   if (e_cov == 0 || (mode < 0 && e_cov < g->e_part / 5)) return 0;
 
-  // 4. virtual-vertex bases: every block holds Nh (+ padding) virtual vertices, padded so that its merge items
-  //    (vertices + edges) are a whole number of super-tiles
-  uint64_t nv_virtual = 0, items = 0;
-  for (uint32_t b = 0; b < NB; ++b) {
-    const uint64_t it = (uint64_t)Nh + hist[b];
-    const uint64_t pad = (shp.super - it % shp.super) % shp.super;
-    g->sb_pb.vbase[b] = (uint32_t)nv_virtual;
-    nv_virtual += Nh + pad;
-    items += it + pad;
-    g->sb_super_end[b] = (uint32_t)(items / shp.super);
-    if (nv_virtual >= 0x7FFFFFF0ull || items / shp.super >= 0xFFFFFFF0ull) return 0;  // too many virtual vertices: keep the plain sweep
+  // 4. panel CSC over virtual vertices (block b, hub h) -> index b * Nh + h: offsets + per-vertex in-degree
+  const uint32_t NV = Nh * NB;
+  StreamBlocks pblk{};
+  pblk.n_blocks = NB;
+  for (uint32_t b = 0; b <= NB; ++b) {
+    g->sb_pb.vbase[b] = b * Nh;
+    pblk.vfirst[b] = b * Nh;
   }
-  g->sb_pb.vbase[NB] = (uint32_t)nv_virtual;
-  const uint32_t NV = (uint32_t)nv_virtual;
-
-  // 5. panel CSC
-  PullLayout& PL = g->sb_panel;
-  PL = PullLayout();
-  PL.n_vtx = NV;
-  PL.e_cnt = e_cov;
+  pblk.ebase[0] = 0;
+  for (uint32_t b = 0; b < NB; ++b) pblk.ebase[b + 1] = pblk.ebase[b] + hist[b];
   uint16_t* d_src16 = nullptr;
   uint32_t* d_vcount = nullptr;
-  LUXB_TRY(dmalloc(&d_src16, e_cov + 32));
-  PL.d_src = d_src16;
-  LUXB_CUDA(cudaMemsetAsync(d_src16, 0, (e_cov + 32) * 2, g->stream));
+  uint64_t* d_vrow = nullptr;
+  LUXB_TRY(tmp.alloc(&d_src16, e_cov + 32));
   LUXB_TRY(tmp.alloc(&d_vcount, (uint64_t)NV + 1));
   LUXB_CUDA(cudaMemsetAsync(d_vcount, 0, ((size_t)NV + 1) * 4, g->stream));
   panel_fill_kernel<<<grid, 256, 0, g->stream>>>(d_key2, d_pay2, e_cov, g->d_src_gather, bs, g->sb_pb, d_src16, d_vcount);
   LUXB_CUDA(cudaGetLastError());
-  LUXB_TRY(dmalloc(&PL.d_row_end, (uint64_t)NV + 4));
-  widen_u32_to_u64_kernel<<<grid, 256, 0, g->stream>>>(d_vcount, PL.d_row_end, NV);
+  LUXB_TRY(tmp.alloc(&d_vrow, (uint64_t)NV + 4));
+  widen_u32_to_u64_kernel<<<grid, 256, 0, g->stream>>>(d_vcount, d_vrow, NV);
   tb = 0;
-  LUXB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, PL.d_row_end, PL.d_row_end, (int)NV, g->stream));
+  LUXB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, d_vrow, d_vrow, (int)NV, g->stream));
   LUXB_TRY(tmp.alloc((char**)&d_scan_tmp, tb + 256));
-  LUXB_CUDA(cub::DeviceScan::InclusiveSum(d_scan_tmp, tb, PL.d_row_end, PL.d_row_end, (int)NV, g->stream));
-  pad_sentinels_kernel<<<1, 32, 0, g->stream>>>(PL.d_row_end, NV);
-  LUXB_CUDA(cudaGetLastError());
+  LUXB_CUDA(cub::DeviceScan::InclusiveSum(d_scan_tmp, tb, d_vrow, d_vrow, (int)NV, g->stream));
   LUXB_CUDA(cudaStreamSynchronize(g->stream));
   tmp.release(d_scan_tmp);
   tmp.release(d_vcount);
+  LUXB_TRY((build_seg_stream<uint16_t, uint16_t>(g, g->sb_panel, d_vrow, NV, d_src16, e_cov, pblk, (uint32_t)shp.stage_edges,
+                                                 (uint32_t)shp.piece, 0, false, g->sb_super_end)));
+  tmp.release(d_vrow);
+  tmp.release(d_src16);
 
-  // 6. main CSC: what is left, in the original (dst, src) order
-  PullLayout& ML = g->sb_main;
-  ML = PullLayout();
-  ML.n_vtx = g->n_part;
-  ML.e_cnt = e_main;
+  // 5. main stream: what is left, in the original (dst, src) order
   uint32_t* d_main_src = nullptr;
-  LUXB_TRY(dmalloc(&d_main_src, e_main + 8));
-  ML.d_src = d_main_src;
-  LUXB_CUDA(cudaMemsetAsync(d_main_src, 0, (e_main + 8) * 4, g->stream));
+  uint64_t* d_main_row = nullptr;
+  LUXB_TRY(tmp.alloc(&d_main_src, e_main + 8));
   main_fill_kernel<<<grid, 256, 0, g->stream>>>(d_pay2 + e_cov, e_main, g->d_src_gather, d_main_src);
-  LUXB_TRY(dmalloc(&ML.d_row_end, (uint64_t)g->n_part + 4));
-  main_indeg_kernel<<<grid, 256, 0, g->stream>>>(g->d_row_end, g->n_part, d_flag, d_hub_idx, d_cov, ML.d_row_end);
+  LUXB_TRY(tmp.alloc(&d_main_row, (uint64_t)g->n_part + 4));
+  main_indeg_kernel<<<grid, 256, 0, g->stream>>>(g->d_row_end, g->n_part, d_flag, d_hub_idx, d_cov, d_main_row);
   LUXB_CUDA(cudaGetLastError());
   tb = 0;
-  LUXB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, ML.d_row_end, ML.d_row_end, (int)g->n_part, g->stream));
+  LUXB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, d_main_row, d_main_row, (int)g->n_part, g->stream));
   LUXB_TRY(tmp.alloc((char**)&d_scan_tmp, tb + 256));
-  LUXB_CUDA(cub::DeviceScan::InclusiveSum(d_scan_tmp, tb, ML.d_row_end, ML.d_row_end, (int)g->n_part, g->stream));
-  pad_sentinels_kernel<<<1, 32, 0, g->stream>>>(ML.d_row_end, g->n_part);
-  uint64_t chk[2] = {0, 0};
-  LUXB_CUDA(cudaMemcpyAsync(&chk[0], ML.d_row_end + g->n_part - 1, 8, cudaMemcpyDeviceToHost, g->stream));
-  LUXB_CUDA(cudaMemcpyAsync(&chk[1], PL.d_row_end + NV - 1, 8, cudaMemcpyDeviceToHost, g->stream));
+  LUXB_CUDA(cub::DeviceScan::InclusiveSum(d_scan_tmp, tb, d_main_row, d_main_row, (int)g->n_part, g->stream));
+  uint64_t chk = 0;
+  LUXB_CUDA(cudaMemcpyAsync(&chk, d_main_row + g->n_part - 1, 8, cudaMemcpyDeviceToHost, g->stream));
   LUXB_CUDA(cudaStreamSynchronize(g->stream));
-  if (chk[0] != e_main || chk[1] != e_cov) { set_error("panel split: offsets do not add up"); return LUXB_ERR_STATE; }
+  if (chk != e_main) { set_error("panel split: offsets do not add up"); return LUXB_ERR_STATE; }
   tmp.release(d_scan_tmp);
   tmp.release(d_key2);
   tmp.release(d_pay2);
+  const SegShapeInfo mshp = kSegMainInfo[g->seg_main_shape];
+  StreamBlocks mblk{};
+  mblk.n_blocks = 1;
+  mblk.vfirst[0] = 0; mblk.vfirst[1] = g->n_part;
+  mblk.ebase[0] = 0; mblk.ebase[1] = e_main;
+  LUXB_TRY((build_seg_stream<uint32_t, uint32_t>(g, g->sb_main, d_main_row, g->n_part, d_main_src, e_main, mblk, (uint32_t)mshp.stage_edges,
+                                                 (uint32_t)mshp.piece, 0, true, nullptr)));
+  tmp.release(d_main_row);
+  tmp.release(d_main_src);
 
-  // 7. tile tables + fix-up scratch; 8. raw panel sums
-  LUXB_TRY(finish_pull_layout(g, PL, (uint32_t)shp.tile));
-  LUXB_TRY(finish_pull_layout(g, ML, (uint32_t)kPullTileOf[g->pull_shape]));
+  // 6. raw panel sums: one slot per (block, hub); slots of (block, hub) pairs without edges stay 0 forever
   LUXB_TRY(dmalloc(&g->d_sb_partial, (uint64_t)NV + 1));
   LUXB_CUDA(cudaMemsetAsync(g->d_sb_partial, 0, ((size_t)NV + 1) * 4, g->stream));
   LUXB_CUDA(cudaStreamSynchronize(g->stream));
@@ -1229,81 +1396,192 @@ static int build_panel_layout(luxb_graph* g) {
   g->stats.panel_blocks = NB;
   if (g->cfg.verbose)
     printf("[luxb rank %d] source-blocked sweep: %u hub destinations (in-degree >= %u) x %u blocks of %u hot sources; panel %llu edges "
-           "(%.1f %%) over %u virtual vertices, main %llu edges\n", g->cfg.rank, Nh, min_indeg, NB, bs, (unsigned long long)e_cov,
-           100.0 * e_cov / g->e_part, NV, (unsigned long long)e_main);
+           "(%.1f %%), main %llu edges\n", g->cfg.rank, Nh, min_indeg, NB, bs, (unsigned long long)e_cov, 100.0 * e_cov / g->e_part,
+           (unsigned long long)e_main);
+  return 0;
+}
+
+// PageRank's sweep structures: the flagged stream(s) of seg.cuh.  LUXB_SWEEP=merge keeps the merge-path tiles of pull.cuh.
+static int build_pagerank_sweep(luxb_graph* g) {
+  g->seg_on = false;
+  g->sb_on = false;
+  if (const char* env = getenv("LUXB_SWEEP")) if (!strcmp(env, "merge")) return 0;
+  if (g->n_part == 0 || g->cfg.zero_copy_edges || g->e_part >= 0xFFFFFFF0ull) return 0;  // zero-copy graphs keep the canonical arrays
+  g->seg_main_shape = env_int("LUXB_SEG_MAIN_SHAPE", 0);
+  if (g->seg_main_shape < 0 || g->seg_main_shape >= kNumSegMain) g->seg_main_shape = 0;
+  g->seg_panel_shape = env_int("LUXB_SEG_PANEL_SHAPE", 0);
+  if (g->seg_panel_shape < 0 || g->seg_panel_shape >= kNumSegPanel) g->seg_panel_shape = 0;
+  LUXB_TRY(build_panel_layout(g));
+  if (!g->sb_on) {
+    free_layout(g->sb_panel);
+    LUXB_TRY(build_plain_seg_layout(g));
+  }
+  g->seg_on = true;
   return 0;
 }
 
 extern "C++" {
-template <class Shape>
-static int launch_panel_shape(luxb_graph* g, const PanelArgs& a) {
-  auto kern = panel_tile_kernel<Shape>;
+template <class Prog, class Shape>
+static int launch_seg_shape(luxb_graph* g, const SegArgs<Prog>& a, int ctas_per_sm) {
+  auto kern = seg_tile_kernel<Prog, Shape>;
   LUXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Shape::kSmemBytes));
-  LUXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  const uint32_t n_super = (a.n_tiles + Shape::kWarps - 1) / Shape::kWarps;
-  const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)g->num_sms, n_super);
+  int carve_pct = (int)std::min<size_t>(100, (ctas_per_sm * (Shape::kSmemBytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+  LUXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve_pct));
+  const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)g->num_sms * ctas_per_sm, a.n_stages);
   kern<<<grid, Shape::kThreads, Shape::kSmemBytes, g->stream>>>(a);
   LUXB_CUDA(cudaGetLastError());
   return 0;
 }
+
+template <class Prog>
+static void fill_seg_args(SegArgs<Prog>& a, const PullLayout& L) {
+  fill_fixup_args(a.p, L);
+  a.p.close_vtx = L.d_close;
+  a.words = L.d_src;
+  a.n_stages = L.n_stages;
+}
 }  // extern "C++"
 
-// one PageRank sweep = panel sweep (shared-memory gathers) + main sweep (L1 gathers) + hub combine
-static int pagerank_sweep_blocked(luxb_graph* g, const float* x_old, float* x_new, const PageRankProgram::Params& prm, int out_replica) {
-  const PullLayout& PL = g->sb_panel;
-  PanelArgs pa{};
-  pa.row_end32 = PL.d_row_end32;
-  pa.src16 = reinterpret_cast<const uint16_t*>(PL.d_src);
-  pa.tile_v = PL.d_tile_v;
-  pa.n_vtx = PL.n_vtx;
-  pa.e_cnt = PL.e_cnt;
-  pa.n_tiles = PL.n_tiles;
-  pa.x_hot = (const float*)g->d_hot;
-  pa.bs = g->sb_bs;
-  pa.n_blocks = g->sb_n_blocks;
-  for (uint32_t b = 0; b < g->sb_n_blocks; ++b) pa.super_end[b] = g->sb_super_end[b];
-  pa.out = g->d_sb_partial;
-  pa.head_partial = (float*)PL.d_head;
-  pa.tail_partial = (float*)PL.d_tail;
-  pa.tile_counter = reinterpret_cast<uint32_t*>(g->d_counters + 4);
-  LUXB_CUDA(cudaMemsetAsync(pa.tile_counter, 0, 4, g->stream));
-  LUXB_TRY(kt_begin(g));
-  switch (g->sb_shape) {
-#define LUXB_CASE_PSHAPE(id, ipt, warps, stages, tab) \
-    case id: LUXB_TRY((launch_panel_shape<PanelShape##id>(g, pa))); break;
-    LUXB_PANEL_SHAPES(LUXB_CASE_PSHAPE)
-    default: set_error("bad panel shape"); return LUXB_ERR_STATE;
+// main (L1) stream of the PageRank sweep: seg kernel + fix-up + vertices without in-edges
+static int launch_seg_main(luxb_graph* g, const PullLayout& L, const float* x_cold, float* out_local, const PageRankProgram::Params& prm,
+                           const uint32_t* hub_bits) {
+  SegArgs<PageRankProgram> a{};
+  fill_seg_args(a, L);
+  a.p.n_part = L.n_vtx;
+  a.p.row_left = g->row_left;
+  a.p.x_old = x_cold;
+  a.p.x_hot = (const float*)g->d_hot;
+  a.p.hot_n = g->hot_n;
+  a.p.out = out_local;
+  a.p.prm = prm;
+  a.p.hub_bits = hub_bits;
+  a.tile_counter = reinterpret_cast<uint32_t*>(g->d_counters + 2);
+  LUXB_CUDA(cudaMemsetAsync(a.tile_counter, 0, 4, g->stream));
+  switch (g->seg_main_shape) {
+#define LUXB_CASE_MSHAPE(id, warps, stages, rounds) \
+    case id: LUXB_TRY((launch_seg_shape<PageRankProgram, SegMain##id>(g, a, g->pull_ctas))); break;
+    LUXB_SEG_MAIN_SHAPES(LUXB_CASE_MSHAPE)
+    default: set_error("bad seg shape"); return LUXB_ERR_STATE;
   }
   g->stats.kernel_launches++;
-  pt_mark(g, 5);
-  PullArgs<PageRankProgram> fa{};
-  fill_fixup_args(fa, PL);
-  fa.out = g->d_sb_partial;
-  fa.raw_out = 1;
-  fa.prm = prm;
-  LUXB_TRY(launch_fixup(g, fa, PL));
+  pt_mark(g, 0);
+  LUXB_TRY(launch_fixup(g, a.p, L));
+  if (L.n_empty) {
+    empties_kernel<PageRankProgram><<<grid_for(L.n_empty, 256, g->num_sms * 8), 256, 0, g->stream>>>(a.p, L.d_empty, L.n_empty);
+    LUXB_CUDA(cudaGetLastError());
+    g->stats.kernel_launches++;
+  }
   pt_mark(g, 1);
-  // main sweep; hub vertices keep their raw sums
-  LUXB_TRY(launch_pull<PageRankProgram>(g, g->sb_main, x_old, (const float*)g->d_hot, g->hot_n, x_new + g->row_left, prm, out_replica,
-                                        g->d_hub_bits, /*timed=*/false));
+  return 0;
+}
+
+// one PageRank sweep = [panel stream (shared-memory gathers) +] main stream (L1 gathers) [+ hub combine]
+static int pagerank_sweep_seg(luxb_graph* g, const float* x_cold, float* x_new, const PageRankProgram::Params& prm) {
+  LUXB_TRY(kt_begin(g));
+  if (g->sb_on) {
+    const PullLayout& PL = g->sb_panel;
+    SegArgs<PageRankProgram> pa{};
+    fill_seg_args(pa, PL);
+    pa.p.x_hot = (const float*)g->d_hot;
+    pa.p.out = g->d_sb_partial;
+    pa.p.raw_out = 1;
+    pa.p.prm = prm;
+    pa.bs = g->sb_bs;
+    pa.n_blocks = g->sb_n_blocks;
+    for (uint32_t b = 0; b < g->sb_n_blocks; ++b) pa.super_end[b] = g->sb_super_end[b];
+    pa.tile_counter = reinterpret_cast<uint32_t*>(g->d_counters + 4);
+    LUXB_CUDA(cudaMemsetAsync(pa.tile_counter, 0, 4, g->stream));
+    switch (g->seg_panel_shape) {
+#define LUXB_CASE_PSHAPE(id, warps, stages, rounds, tab) \
+      case id: LUXB_TRY((launch_seg_shape<PageRankProgram, SegPanel##id>(g, pa, 1))); break;
+      LUXB_SEG_PANEL_SHAPES(LUXB_CASE_PSHAPE)
+      default: set_error("bad panel shape"); return LUXB_ERR_STATE;
+    }
+    g->stats.kernel_launches++;
+    pt_mark(g, 5);
+    LUXB_TRY(launch_fixup(g, pa.p, PL));
+    pt_mark(g, 1);
+  }
+  LUXB_TRY(launch_seg_main(g, g->sb_main, x_cold, x_new + g->row_left, prm, g->sb_on ? g->d_hub_bits : nullptr));
   LUXB_TRY(kt_end(g));
-  CombineArgs<PageRankProgram> ca{};
-  ca.hub_vtx = g->d_hub_vtx;
-  ca.n_hub = g->sb_n_hub;
-  ca.n_blocks = g->sb_n_blocks;
-  ca.row_left = g->row_left;
-  ca.pb = g->sb_pb;
-  ca.partial = g->d_sb_partial;
-  ca.out = x_new + g->row_left;
-  ca.prm = prm;
-  ca.n_peers = 0;
-  if (out_replica >= 0 && g->p2p_ready && g->cfg.exchange == LUXB_EXCHANGE_P2P_FUSED)
-    for (int p = 0; p < g->P; ++p)
-      if (p != g->cfg.rank) ca.peer_out[ca.n_peers++] = reinterpret_cast<float*>(g->peer_val[out_replica][p]) + g->row_left;
-  combine_hub_kernel<PageRankProgram><<<grid_for(g->sb_n_hub, 256, g->num_sms * 8), 256, 0, g->stream>>>(ca);
+  if (g->sb_on) {
+    CombineArgs<PageRankProgram> ca{};
+    ca.hub_vtx = g->d_hub_vtx;
+    ca.n_hub = g->sb_n_hub;
+    ca.n_blocks = g->sb_n_blocks;
+    ca.row_left = g->row_left;
+    ca.pb = g->sb_pb;
+    ca.partial = g->d_sb_partial;
+    ca.out = x_new + g->row_left;
+    ca.prm = prm;
+    ca.n_peers = 0;
+    combine_hub_kernel<PageRankProgram><<<grid_for(g->sb_n_hub, 256, g->num_sms * 8), 256, 0, g->stream>>>(ca);
+    LUXB_CUDA(cudaGetLastError());
+    g->stats.kernel_launches++;
+    pt_mark(g, 6);
+  }
+  return 0;
+}
+
+// After a sweep (or luxb_set_values): x_new holds this rank's final slice in natural order.  Make it visible to the
+// next sweep of every rank: refresh the hot copies and, on several ranks, run the PACKED exchange — only vertices that are
+// ever gathered travel (build.cuh), as one balanced all-gather: each rank packs its share into XT[new], DMA-copies the
+// pieces that fall into a peer's EQUAL chunk straight into that peer's XT[new] over NVLink, and after a 4-byte barrier
+// ncclAllGather distributes the equal chunks (edge-balanced partitions own very different numbers of vertices — RMAT-27 at
+// 8 GPUs: rank 7 owns 40 % — so owner broadcasts would be bound by the biggest owner's egress).
+static int pagerank_publish(luxb_graph* g, float* x_new) {
+  const int me = g->cfg.rank;
+  const int grid = g->num_sms * 8;
+  if (g->P == 1 || !g->packed) {
+    if (g->P > 1) { LUXB_TRY(allgather_slices(g, x_new, 4)); pt_mark(g, 3); }  // graphs without a hot set (tiny): plain all-gather
+    if (g->hot_n) {
+      hot_refresh_kernel<float><<<grid_for(g->hot_n, 256, grid), 256, 0, g->stream>>>((float*)g->d_hot, x_new, g->d_hot_order, 0, g->hot_n);
+      LUXB_CUDA(cudaGetLastError());
+      g->stats.kernel_launches++;
+      pt_mark(g, 2);
+    }
+    return 0;
+  }
+  float* XTn = g->d_xt[1 - g->cur_xt];
+  const uint32_t H = g->hot_n;
+  const uint32_t nh_me = g->hot_off[me + 1] - g->hot_off[me], nc_me = g->cold_off[me + 1] - g->cold_off[me];
+  if (nh_me + nc_me) {
+    pack_values_kernel<float><<<grid_for((uint64_t)nh_me + nc_me, 256, grid), 256, 0, g->stream>>>(
+        x_new + g->row_left, g->d_pack_list, nh_me, nc_me, XTn + g->hot_off[me], XTn + H + g->cold_off[me]);
+    LUXB_CUDA(cudaGetLastError());
+    g->stats.kernel_launches++;
+  }
+  if (g->p2p_ready && g->cfg.exchange != LUXB_EXCHANGE_NCCL) {
+    const uint64_t C = g->xt_chunk;
+    const uint64_t rng[2][2] = {{g->hot_off[me], g->hot_off[me + 1]}, {(uint64_t)H + g->cold_off[me], (uint64_t)H + g->cold_off[me + 1]}};
+    for (int r = 0; r < 2; ++r)
+      for (int k = 0; k < g->P; ++k) {
+        if (k == me) continue;
+        const uint64_t lo = std::max<uint64_t>(rng[r][0], k * C), hi = std::min<uint64_t>(rng[r][1], (k + 1) * C);
+        if (lo < hi)
+          LUXB_CUDA(cudaMemcpyAsync(reinterpret_cast<float*>(g->peer_xt[1 - g->cur_xt][k]) + lo, XTn + lo, (hi - lo) * 4, cudaMemcpyDefault,
+                                    g->stream));
+      }
+    pt_mark(g, 3);
+    LUXB_TRY(p2p_barrier(g));
+    LUXB_NCCL(nccl().AllGather(XTn + me * C, XTn, C, ncclFloat32, g->comm, g->stream));
+    pt_mark(g, 4);
+  } else {
+    LUXB_NCCL(nccl().GroupStart());
+    for (int p = 0; p < g->P; ++p) {
+      const uint32_t nh = g->hot_off[p + 1] - g->hot_off[p], nc = g->cold_off[p + 1] - g->cold_off[p];
+      if (nh) LUXB_NCCL(nccl().Broadcast(XTn + g->hot_off[p], XTn + g->hot_off[p], nh, ncclFloat32, p, g->comm, g->stream));
+      if (nc) LUXB_NCCL(nccl().Broadcast(XTn + H + g->cold_off[p], XTn + H + g->cold_off[p], nc, ncclFloat32, p, g->comm, g->stream));
+    }
+    LUXB_NCCL(nccl().GroupEnd());
+    pt_mark(g, 3);
+  }
+  hot_permute_kernel<float><<<grid_for(H, 256, grid), 256, 0, g->stream>>>((float*)g->d_hot, XTn, g->d_zperm, H);
   LUXB_CUDA(cudaGetLastError());
   g->stats.kernel_launches++;
-  pt_mark(g, 6);
+  pt_mark(g, 2);
+  g->cur_xt ^= 1;
+  g->replica_stale = true;
   return 0;
 }
 
@@ -1314,58 +1592,14 @@ static int pagerank_iteration(luxb_graph* g) {
   prm.deg = g->d_deg;
   float* x_old = (float*)g->d_val[g->cur];
   float* x_new = (float*)g->d_val[1 - g->cur];
-  const bool p2p = g->P > 1 && g->p2p_ready && g->cfg.exchange != LUXB_EXCHANGE_NCCL;
-  const bool fused = p2p && g->cfg.exchange == LUXB_EXCHANGE_P2P_FUSED;
-  if (g->sb_on) {
-    LUXB_TRY(pagerank_sweep_blocked(g, x_old, x_new, prm, fused ? 1 - g->cur : -1));
+  const float* x_cold = g->packed ? g->d_xt[g->cur_xt] + g->hot_n : x_old;
+  if (g->seg_on) {
+    LUXB_TRY(pagerank_sweep_seg(g, x_cold, x_new, prm));
   } else {
-    LUXB_TRY(launch_pull<PageRankProgram>(g, base_layout(g, g->hot_n ? g->d_src_gather : g->d_src), x_old, (const float*)g->d_hot,
-                                          g->hot_n, x_new + g->row_left, prm, fused ? 1 - g->cur : -1));
+    LUXB_TRY(launch_pull<PageRankProgram>(g, base_layout(g, g->hot_n ? g->d_src_gather : g->d_src), x_old, x_cold, (const float*)g->d_hot,
+                                          g->hot_n, x_new + g->row_left, prm));
   }
-  const int me = g->cfg.rank;
-  if (p2p && !fused) {
-    // Balanced all-gather.  Edge-balanced partitions own very different numbers of vertices (RMAT-27 at P = 8:
-    // rank 7 owns ~40 %), so "every owner sends its slice to everyone" is bound by the biggest owner's egress.
-    // Step 1: re-chunk — each rank copies the parts of its slice that fall into peer k's EQUAL chunk
-    //         [k*C, (k+1)*C) straight into k's new replica (DMA over NVLink, at most its own slice once);
-    // Step 2: after a barrier, ncclAllGather of the equal chunks in place (NVLS / ring at full bus bandwidth).
-    const uint64_t C = g->ag_chunk;
-    const uint64_t s0 = g->row_left, s1 = (uint64_t)g->row_left + g->n_part;
-    for (int k = 0; k < g->P; ++k) {
-      if (k == me) continue;
-      uint64_t lo = std::max<uint64_t>(s0, k * C), hi = std::min<uint64_t>(s1, (k + 1) * C);
-      if (lo < hi)
-        LUXB_CUDA(cudaMemcpyAsync(reinterpret_cast<float*>(g->peer_val[1 - g->cur][k]) + lo, x_new + lo, (hi - lo) * 4,
-                                  cudaMemcpyDefault, g->stream));
-    }
-    pt_mark(g, 3);
-    LUXB_TRY(p2p_barrier(g));
-    LUXB_NCCL(nccl().AllGather(x_new + me * C, x_new, C, ncclFloat32, g->comm, g->stream));
-    pt_mark(g, 4);
-    if (g->hot_n) {  // each rank refreshes 1/P of the hot copies, then the hot buffer is all-gathered the same way
-      const uint64_t HC = g->hot_chunk;
-      uint32_t h0 = (uint32_t)std::min<uint64_t>(me * HC, g->hot_n), h1 = (uint32_t)std::min<uint64_t>((me + 1) * HC, g->hot_n);
-      if (h1 > h0) {
-        hot_refresh_kernel<float><<<grid_for(h1 - h0, 256, g->num_sms * 8), 256, 0, g->stream>>>((float*)g->d_hot, x_new, g->d_hot_order, h0, h1);
-        g->stats.kernel_launches++;
-      }
-      LUXB_NCCL(nccl().AllGather((float*)g->d_hot + me * HC, g->d_hot, HC, ncclFloat32, g->comm, g->stream));
-      LUXB_CUDA(cudaGetLastError());
-      pt_mark(g, 2);
-    }
-  } else {
-    if (g->P > 1) {
-      if (fused) LUXB_TRY(p2p_barrier(g));
-      else LUXB_TRY(allgather_slices(g, x_new, 4));
-      pt_mark(g, 3);
-    }
-    if (g->hot_n) {  // every rank refreshes its hot copies (in place) from the now complete new values
-      hot_refresh_kernel<float><<<grid_for(g->hot_n, 256, g->num_sms * 8), 256, 0, g->stream>>>((float*)g->d_hot, x_new, g->d_hot_order, 0, g->hot_n);
-      LUXB_CUDA(cudaGetLastError());
-      g->stats.kernel_launches++;
-      pt_mark(g, 2);
-    }
-  }
+  LUXB_TRY(pagerank_publish(g, x_new));
   g->cur ^= 1;
   g->stats.edges_processed += g->e_part;
   return 0;
@@ -1433,8 +1667,8 @@ static int label_iteration(luxb_graph* g) {
       hot_refresh_kernel<uint32_t><<<grid_for(g->hot_n, 256, g->num_sms * 8), 256, 0, g->stream>>>((uint32_t*)g->d_hot, lab, g->d_hot_order, 0, g->hot_n);
       g->stats.kernel_launches++;
     }
-    LUXB_TRY(launch_pull<Prog>(g, base_layout(g, g->hot_n ? g->d_src_gather : g->d_src), lab, (const uint32_t*)g->d_hot, g->hot_n,
-                               g->d_cur, prm, -1));
+    LUXB_TRY(launch_pull<Prog>(g, base_layout(g, g->hot_n ? g->d_src_gather : g->d_src), lab, lab, (const uint32_t*)g->d_hot, g->hot_n,
+                               g->d_cur, prm));
     g->stats.edges_processed += g->e_part;
     g->stats.pull_iterations++;
   } else if (g->n_part && old_size) {
@@ -1638,14 +1872,52 @@ int luxb_run_to_convergence(luxb_graph* g, int max_iters, int* iters_out) {
   return 0;
 }
 
+// PageRank on several ranks exchanges only the packed transfer array every iteration: the natural-order replica is
+// completed on demand (collective: every rank must make the same call)
+static int refresh_replica(luxb_graph* g) {
+  if (g->cfg.app == LUXB_PAGERANK && g->P > 1 && g->replica_stale) {
+    LUXB_TRY(allgather_slices(g, g->d_val[g->cur], 4));
+    g->replica_stale = false;
+  }
+  return 0;
+}
+
 int luxb_get_values(luxb_graph* g, void* host_out, size_t bytes) {
   LUXB_ARG(g && host_out, "NULL argument");
   if (!g->inited) { set_error("luxb_get_values before luxb_init"); return LUXB_ERR_STATE; }
   size_t need = (size_t)g->nv * g->vbytes;
   LUXB_ARG(bytes == need, "buffer is %zu bytes, vertex values need %zu", bytes, need);
   LUXB_CUDA(cudaSetDevice(g->cfg.device));
+  LUXB_TRY(refresh_replica(g));
   const char* srcp = (const char*)((g->cfg.app == LUXB_CC || g->cfg.app == LUXB_SSSP) ? g->d_val[0] : g->d_val[g->cur]);
   LUXB_CUDA(cudaMemcpyAsync(host_out, srcp, need, cudaMemcpyDeviceToHost, g->stream));
+  LUXB_CUDA(cudaStreamSynchronize(g->stream));
+  return 0;
+}
+
+int luxb_get_local_values(luxb_graph* g, void* host_out, size_t bytes) {
+  LUXB_ARG(g && (host_out || g->n_part == 0), "NULL argument");
+  if (!g->inited) { set_error("luxb_get_local_values before luxb_init"); return LUXB_ERR_STATE; }
+  size_t need = (size_t)g->n_part * g->vbytes;
+  LUXB_ARG(bytes == need, "buffer is %zu bytes, this rank's %u vertex values need %zu", bytes, g->n_part, need);
+  LUXB_CUDA(cudaSetDevice(g->cfg.device));
+  const char* base = (const char*)((g->cfg.app == LUXB_CC || g->cfg.app == LUXB_SSSP) ? g->d_val[0] : g->d_val[g->cur]);
+  if (need) LUXB_CUDA(cudaMemcpyAsync(host_out, base + (size_t)g->row_left * g->vbytes, need, cudaMemcpyDeviceToHost, g->stream));
+  LUXB_CUDA(cudaStreamSynchronize(g->stream));
+  return 0;
+}
+
+// values of the vertices are in place in the current replica (whole array, or only this rank's slice): make them the
+// state the next iteration starts from on every rank
+static int values_installed(luxb_graph* g, bool whole_array) {
+  const bool labels = g->cfg.app == LUXB_CC || g->cfg.app == LUXB_SSSP;
+  if (g->cfg.app == LUXB_PAGERANK) {
+    LUXB_TRY(pagerank_publish(g, (float*)g->d_val[g->cur]));
+    g->replica_stale = !whole_array && g->P > 1;
+  } else {
+    if (!whole_array && g->P > 1) LUXB_TRY(allgather_slices(g, labels ? g->d_val[0] : g->d_val[g->cur], g->vbytes));
+    if (labels) LUXB_TRY(reset_label_state(g, true));
+  }
   LUXB_CUDA(cudaStreamSynchronize(g->stream));
   return 0;
 }
@@ -1659,11 +1931,19 @@ int luxb_set_values(luxb_graph* g, const void* host_in, size_t bytes) {
   const bool labels = g->cfg.app == LUXB_CC || g->cfg.app == LUXB_SSSP;
   char* dstp = (char*)(labels ? g->d_val[0] : g->d_val[g->cur]);
   LUXB_CUDA(cudaMemcpyAsync(dstp, host_in, need, cudaMemcpyHostToDevice, g->stream));
-  if (g->hot_n)
-    hot_refresh_kernel<float><<<grid_for(g->hot_n, 256, g->num_sms * 8), 256, 0, g->stream>>>((float*)g->d_hot, (const float*)dstp, g->d_hot_order, 0, g->hot_n);
-  if (labels) LUXB_TRY(reset_label_state(g, true));
-  LUXB_CUDA(cudaStreamSynchronize(g->stream));
-  return 0;
+  return values_installed(g, true);
+}
+
+int luxb_set_local_values(luxb_graph* g, const void* host_in, size_t bytes) {
+  LUXB_ARG(g && (host_in || g->n_part == 0), "NULL argument");
+  if (!g->inited) { set_error("luxb_set_local_values before luxb_init"); return LUXB_ERR_STATE; }
+  size_t need = (size_t)g->n_part * g->vbytes;
+  LUXB_ARG(bytes == need, "buffer is %zu bytes, this rank's %u vertex values need %zu", bytes, g->n_part, need);
+  LUXB_CUDA(cudaSetDevice(g->cfg.device));
+  const bool labels = g->cfg.app == LUXB_CC || g->cfg.app == LUXB_SSSP;
+  char* dstp = (char*)(labels ? g->d_val[0] : g->d_val[g->cur]);
+  if (need) LUXB_CUDA(cudaMemcpyAsync(dstp + (size_t)g->row_left * g->vbytes, host_in, need, cudaMemcpyHostToDevice, g->stream));
+  return values_installed(g, false);
 }
 
 int luxb_check(luxb_graph* g, uint64_t* mistakes_out) {
@@ -1740,7 +2020,7 @@ __global__ void debug_gather_kernel(const uint32_t* __restrict__ idx, const floa
 }
 
 int luxb_debug_gather_ms(luxb_graph* g, int packed, float* ms_out) {
-  LUXB_ARG(g && ms_out && g->inited && g->cfg.app == LUXB_PAGERANK, "needs an initialised PageRank graph");
+  LUXB_ARG(g && ms_out && g->inited && g->cfg.app == LUXB_PAGERANK && g->P == 1, "needs an initialised single-rank PageRank graph");
   LUXB_CUDA(cudaSetDevice(g->cfg.device));
   const bool use_hot = packed && g->hot_n;
   const uint32_t* idx = use_hot ? g->d_src_gather : g->d_src;
@@ -1798,14 +2078,7 @@ void luxb_close(luxb_graph* g) {
   cudaSetDevice(g->cfg.device);
   if (g->stream) cudaStreamSynchronize(g->stream);
   if (g->d_hot) cudaCtxResetPersistingL2Cache();  // release the lines pinned for the hot copies
-  if (g->p2p_ready)
-    for (int p = 0; p < g->P; ++p)
-      if (p != g->cfg.rank)
-        for (int k = 0; k < 2; ++k)
-          if (g->peer_val[k][p]) cudaIpcCloseMemHandle(g->peer_val[k][p]);
-  if (g->p2p_ready)
-    for (int p = 0; p < g->P; ++p)
-      if (p != g->cfg.rank && g->peer_hot[p]) cudaIpcCloseMemHandle(g->peer_hot[p]);
+  p2p_unmap(g);
   if (g->comm) nccl().CommDestroy(g->comm);
   void* ptrs[] = {g->d_row_end, g->d_row_end32, g->d_src, g->d_weight, g->d_tile_v, g->d_head, g->d_tail, g->d_deg, g->d_val[0], g->d_val[1],
                   g->d_cur, g->d_out_end, g->d_out_dst, g->d_fq_all, g->d_fq_new, g->d_fq_tmp, g->d_hdr_all, g->d_counters,
@@ -1821,6 +2094,7 @@ void luxb_close(luxb_graph* g) {
   if (g->d_hub_vtx) cudaFree(g->d_hub_vtx);
   if (g->d_hub_bits) cudaFree(g->d_hub_bits);
   if (g->d_sb_partial) cudaFree(g->d_sb_partial);
+  for (void* q : {(void*)g->d_zperm, (void*)g->d_pack_list, (void*)g->d_xt[0], (void*)g->d_xt[1]}) if (q) cudaFree(q);
   if (g->h_hdr) cudaFreeHost(g->h_hdr);
   if (g->h_scratch) cudaFreeHost(g->h_scratch);
   for (cudaEvent_t e : g->kt_events) cudaEventDestroy(e);

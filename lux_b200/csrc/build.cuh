@@ -223,9 +223,9 @@ __device__ __forceinline__ int owner_of(const PartTable& pt, uint32_t v) {
   return o;
 }
 
-// keys/ids of the hot vertices only (compacted with a warp-aggregated cursor).  key = owner partition in the high
-// word, inverted out-degree in the low word: ascending key = grouped by owner, hottest first inside each group
-// (each rank can then refresh and push ITS segment of the hot copies as one contiguous slice).
+// keys/ids of the hot vertices only (compacted with a warp-aggregated cursor).  key = inverted out-degree: ascending
+// (key, id) = GLOBAL hotness order (the source-blocked sweep cuts it into blocks, panel.cuh); per_owner counts how many
+// hot vertices each partition owns (the packed exchange ships them grouped by owner, see owner_keys_kernel).
 __global__ void hot_select_kernel(const uint32_t* __restrict__ deg, uint32_t nv, uint32_t tau, PartTable pt, unsigned int* cursor,
                                   unsigned int* __restrict__ per_owner, uint64_t* __restrict__ keys, uint32_t* __restrict__ ids,
                                   uint32_t capacity) {
@@ -242,7 +242,7 @@ __global__ void hot_select_kernel(const uint32_t* __restrict__ deg, uint32_t nv,
         unsigned pos = base + __popc(m & ((1u << lane) - 1));
         int o = owner_of(pt, (uint32_t)v);
         atomicAdd(per_owner + o, 1u);
-        if (pos < capacity) { keys[pos] = ((uint64_t)o << 32) | (0xFFFFFFFFu - deg[v]); ids[pos] = (uint32_t)v; }
+        if (pos < capacity) { keys[pos] = 0xFFFFFFFFu - deg[v]; ids[pos] = (uint32_t)v; }
       }
     }
   }
@@ -263,6 +263,53 @@ __global__ void hot_refresh_kernel(T* __restrict__ hot, const T* __restrict__ na
                                    uint32_t h1) {
   for (uint64_t h = (uint64_t)h0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < h1; h += (uint64_t)gridDim.x * blockDim.x)
     hot[h] = nat[order[h]];
+}
+
+// ---- packed exchange (PageRank, nranks > 1) -------------------------------------------------------------------------
+// Only vertices that are ever gathered (out-degree > 0) are exchanged, in a packed transfer array
+//   XT = [ hot values grouped by owner (H) | cold-active values (0 < deg < tau) in natural id order = grouped by owner ]
+// so that every owner's share is two contiguous ranges.  Cold gathers index XT's cold part directly; the hot part is
+// permuted into the globally hotness-ordered copy the kernels gather from (zperm).  Reference precedent: only the
+// in-neighbours of a partition are refreshed (in_vtxs / load_kernel, pagerank_gpu.cu:229-242, :34-47).
+__global__ void cold_flag_kernel(const uint32_t* __restrict__ deg, uint32_t nv, uint32_t tau, uint32_t* __restrict__ flag) {
+  for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (uint64_t)gridDim.x * blockDim.x)
+    flag[v] = (deg[v] > 0 && deg[v] < tau) ? 1u : 0u;
+}
+__global__ void gather_map_compact_kernel(uint32_t* __restrict__ map, const uint32_t* __restrict__ coldrank, uint32_t nv, uint32_t H) {
+  for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (uint64_t)gridDim.x * blockDim.x) map[v] = H + coldrank[v];
+}
+__global__ void owner_keys_kernel(const uint32_t* __restrict__ hot_order, uint32_t H, PartTable pt, uint32_t* __restrict__ keys,
+                                  uint32_t* __restrict__ ranks) {
+  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < H; r += (uint64_t)gridDim.x * blockDim.x) {
+    keys[r] = (uint32_t)owner_of(pt, hot_order[r]);
+    ranks[r] = (uint32_t)r;
+  }
+}
+// pack list of this rank: local indices of [its hot vertices in transfer order | its cold-active vertices ascending]
+__global__ void pack_list_hot_kernel(const uint32_t* __restrict__ hot_order, const uint32_t* __restrict__ zperm, uint32_t h0, uint32_t n,
+                                     uint32_t row_left, uint32_t* __restrict__ list) {
+  for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x)
+    list[k] = hot_order[zperm[h0 + k]] - row_left;
+}
+__global__ void pack_list_cold_kernel(const uint32_t* __restrict__ flag, const uint32_t* __restrict__ coldrank, uint32_t row_left,
+                                      uint32_t n_part, uint32_t c0, uint32_t* __restrict__ list) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_part; i += (uint64_t)gridDim.x * blockDim.x)
+    if (flag[row_left + i]) list[coldrank[row_left + i] - c0] = (uint32_t)i;
+}
+// per iteration: dst[k] = x_local[list[k]]
+template <class T>
+__global__ void pack_values_kernel(const T* __restrict__ x_local, const uint32_t* __restrict__ list, uint32_t n_hot, uint32_t n_cold,
+                                   T* __restrict__ dst_hot, T* __restrict__ dst_cold) {
+  const uint64_t n = (uint64_t)n_hot + n_cold;
+  for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
+    const T v = x_local[list[k]];
+    if (k < n_hot) dst_hot[k] = v; else dst_cold[k - n_hot] = v;
+  }
+}
+// hot part of the transfer array (owner-grouped) -> globally hotness-ordered copy
+template <class T>
+__global__ void hot_permute_kernel(T* __restrict__ hot, const T* __restrict__ xt_hot, const uint32_t* __restrict__ zperm, uint32_t H) {
+  for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < H; k += (uint64_t)gridDim.x * blockDim.x) hot[zperm[k]] = xt_hot[k];
 }
 
 // P2P push exchange: copy up to two contiguous regions of this rank's buffers to the same offsets of every peer's

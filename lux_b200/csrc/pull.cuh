@@ -73,6 +73,8 @@ struct PullArgs {
   // peer stores) — combine_hub_kernel finishes them; raw_out != 0 does that for every vertex (the panel CSC's fix-up)
   const uint32_t* hub_bits;
   int raw_out;
+  // flagged segmented-scan sweep (seg.cuh): tile_v counts HEADS, and head j completes vertex close_vtx[j]
+  const uint32_t* close_vtx;
   int n_peers;                                        // P2P exchange: peers' slice pointers (local index)
   typename Prog::Vertex* peer_out[LUXB_MAX_PEERS];
 };
@@ -433,7 +435,12 @@ __global__ void __launch_bounds__(kFixBlock) pull_fixup_apply_kernel(const __gri
   Wide c = a.carry[t];
   if (!a.carry_flag[t]) c = Prog::wcombine(a.block_agg[blockIdx.x], c);
   Wide totalw = Prog::wcombine(c, Prog::widen(a.head_partial[t]));
-  store_vertex<Prog>(a, i0, Prog::narrow(totalw));
+  uint32_t v = i0;
+  if (a.close_vtx) {
+    v = a.close_vtx[i0];
+    if (v == 0xFFFFFFFFu) return;  // a dummy (padding) vertex
+  }
+  store_vertex<Prog>(a, v, Prog::narrow(totalw));
 }
 
 }  // namespace luxb

@@ -5,6 +5,7 @@
 #include "comm.h"
 #include "common.cuh"
 #include "panel.cuh"
+#include "seg.cuh"
 
 // one CSC swept by a merge-path tile kernel, with its tile table and fix-up scratch
 struct PullLayout {
@@ -22,6 +23,12 @@ struct PullLayout {
   void* d_block_agg = nullptr;
   uint32_t* d_block_flag = nullptr;
   uint32_t n_fix_blocks = 0;
+  // flagged stream (seg.cuh): d_src holds the words, d_tile_v the heads before each piece, n_tiles the pieces
+  uint32_t* d_close = nullptr;      // [1 + heads] vertex completed by each head
+  uint32_t* d_empty = nullptr;      // vertices without edges in this stream
+  uint32_t n_empty = 0;
+  uint32_t n_stages = 0;
+  uint64_t n_words = 0;
 };
 
 // dev aid: LUXB_PHASE_TIMING=1 prints the mean device time of each phase of a PageRank iteration at luxb_close
@@ -84,6 +91,17 @@ struct luxb_graph {
   uint32_t hot_off[LUXB_MAX_PARTS + 1]{};  // hot slots owned by partition p: [hot_off[p], hot_off[p+1])
   uint32_t* d_hot_order = nullptr;   // [hot_n] vertex id held by each hot slot (descending out-degree)
   uint32_t* d_src_gather = nullptr;  // [e_part + 8] source ids rewritten as indices into Z
+  // packed exchange (PageRank, nranks > 1): transfer arrays XT[2] = [hot by owner (hot_n) | cold-active by id (cold_n)]
+  bool packed = false;
+  uint32_t cold_n = 0;                       // vertices with 0 < out-degree < tau (all partitions)
+  uint32_t cold_off[LUXB_MAX_PARTS + 1]{};   // cold-active vertices owned by partition p: [cold_off[p], cold_off[p+1])
+  uint32_t* d_zperm = nullptr;               // [hot_n] global hot rank of the k-th entry of XT's hot part
+  uint32_t* d_pack_list = nullptr;           // local indices of this rank's [hot | cold-active] vertices in transfer order
+  float* d_xt[2] = {nullptr, nullptr};
+  int cur_xt = 0;
+  uint64_t xt_chunk = 0;                     // equal chunk (elements) of the balanced all-gather over XT
+  void* peer_xt[2][LUXB_MAX_PARTS]{};
+  bool replica_stale = false;                // natural-order replica holds only this rank's slice (gathered on demand)
   // push apps
   uint32_t* d_cur = nullptr;       // [n_part] working labels of this partition
   uint64_t* d_out_end = nullptr;   // [nv] CSR-by-source end offsets over this partition's edges
@@ -112,6 +130,8 @@ struct luxb_graph {
   uint64_t ag_chunk = 0, hot_chunk = 0;  // equal chunk sizes (elements) of the balanced all-gather
 
   // source-blocked PageRank sweep (panel.cuh): hub destinations x hot source blocks in shared memory
+  bool seg_on = false;             // PageRank sweeps the flagged stream(s) of seg.cuh (sb_main [+ sb_panel])
+  int seg_main_shape = 0, seg_panel_shape = 0;
   bool sb_on = false;
   PullLayout sb_main, sb_panel;
   uint32_t sb_n_hub = 0, sb_n_blocks = 0, sb_bs = 0, sb_n_src = 0;

@@ -1,5 +1,6 @@
 """Dev tool: sweep the source-blocked sweep's parameters (panel.cuh) on one GPU at RMAT-<scale>.
-usage: sweep_panel.py [scale] ["SHAPE:BLOCKS:MIN_INDEG[:BS[:PULL_SHAPE[:PULL_CTAS]]],..."]   (SHAPE = off -> plain sweep)
+usage: sweep_panel.py [scale] ["PANEL_SHAPE:BLOCKS:MIN_INDEG[:BS[:MAIN_SHAPE[:MAIN_CTAS]]],..."]
+       PANEL_SHAPE = off -> flagged stream without the split (then MAIN_SHAPE / MAIN_CTAS are fields 4 / 5); merge -> pull.cuh tiles
 Prints per configuration: panel coverage, ms/iteration, the per-phase device times (LUXB_PHASE_TIMING) and a one-step
 parity check against the oracle on pseudo-random destination blocks."""
 import os
@@ -13,22 +14,24 @@ import lux_b200 as L  # noqa: E402
 import oracle as O  # noqa: E402
 
 scale = int(sys.argv[1]) if len(sys.argv) > 1 else 27
-cfgs = sys.argv[2].split(",") if len(sys.argv) > 2 else ["off", "0:48:96", "0:48:48", "0:24:48", "1:40:80", "2:48:96", "3:48:96", "4:48:96"]
+cfgs = sys.argv[2].split(",") if len(sys.argv) > 2 else ["merge", "off", "off::::1", "off::::3:2", "0:48:64", "1:48:64", "2:48:64", "1:64:32", "1:32:64"]
 nv, ne = 1 << scale, 16 << scale
 blk = None
 for c in cfgs:
     f = c.split(":")
-    for k in ("LUXB_SB_SHAPE", "LUXB_SB_BLOCKS", "LUXB_SB_MIN_INDEG", "LUXB_SB_BS", "LUXB_PULL_SHAPE", "LUXB_PULL_CTAS"):
+    for k in ("LUXB_SEG_PANEL_SHAPE", "LUXB_SB_BLOCKS", "LUXB_SB_MIN_INDEG", "LUXB_SB_BS", "LUXB_SEG_MAIN_SHAPE", "LUXB_PULL_CTAS", "LUXB_SWEEP"):
         os.environ.pop(k, None)
-    if f[0] == "off":
+    if f[0] == "merge":
+        os.environ["LUXB_SWEEP"] = "merge"
+    elif f[0] == "off":
         os.environ["LUXB_SB"] = "0"
     else:
         os.environ["LUXB_SB"] = "1"
-        os.environ["LUXB_SB_SHAPE"], os.environ["LUXB_SB_BLOCKS"], os.environ["LUXB_SB_MIN_INDEG"] = f[0], f[1], f[2]
+        os.environ["LUXB_SEG_PANEL_SHAPE"], os.environ["LUXB_SB_BLOCKS"], os.environ["LUXB_SB_MIN_INDEG"] = f[0], f[1], f[2]
         if len(f) > 3 and f[3]:
             os.environ["LUXB_SB_BS"] = f[3]
     if len(f) > 4 and f[4]:
-        os.environ["LUXB_PULL_SHAPE"] = f[4]
+        os.environ["LUXB_SEG_MAIN_SHAPE"] = f[4]
     if len(f) > 5 and f[5]:
         os.environ["LUXB_PULL_CTAS"] = f[5]
     with L.LuxGraph.from_rmat(scale, nv, ne, 27) as g:

@@ -32,7 +32,11 @@ def main():
 
     # ---- partition table must equal the reference greedy split (oracle) on every rank ----
     cnt, rl, rr, cl, _, _ = O.partition(row_end, ne, world)
-    for exchange, ename in ((L.EXCHANGE_NCCL, "nccl"), (L.EXCHANGE_P2P, "p2p"), (L.EXCHANGE_P2P_FUSED, "p2p_fused")):
+    ref6 = O.pagerank(row_end, src, 6)
+    for exchange, ename, sb in ((L.EXCHANGE_NCCL, "nccl", "0"), (L.EXCHANGE_P2P, "p2p", "0"), (L.EXCHANGE_P2P, "p2p+panel", "1"),
+                                (L.EXCHANGE_NCCL, "nccl+panel", "1")):
+        # sb = "1": force the source-blocked split on every rank (small blocks / thresholds), see tests/test_gpu_panel.py
+        os.environ.update({"LUXB_SB": sb, "LUXB_SB_BS": "64", "LUXB_SB_MIN_INDEG": "4"})
         g = L.LuxGraph.from_rmat(scale, nv, ne, seed, rank=rank, nranks=world, device=local, exchange=exchange)
         b = g.bounds()
         report("partition[%s]" % ename, b["found"] == cnt and np.array_equal(b["row_left"], rl) and
@@ -40,14 +44,28 @@ def main():
         g.comm_init_torch()
         g.init()
         if exchange != L.EXCHANGE_NCCL:
-            g.p2p_connect_torch()
+            report("p2p_connect[%s]" % ename, g.p2p_connect_torch())
         g.iterate(6)
-        x = g.values()
-        ref = O.pagerank(row_end, src, 6)
-        err = (np.abs(x - ref) / np.abs(ref)).max()
+        x = g.values()  # collective: completes the natural-order replica (PageRank exchanges only the packed values)
+        err = (np.abs(x - ref6) / np.abs(ref6)).max()
         report("pagerank[%s] world=%d" % (ename, world), err <= 1e-6, "max rel err %.2e" % err)
+        # every rank's own slice through the local API, then restart from it: 3 + 3 iterations = 6
+        g2_lo, g2_n = g.local_range()
+        mine = g.local_values()
+        report("local_values[%s]" % ename, np.array_equal(mine, x[g2_lo:g2_lo + g2_n]))
+        x3 = O.pagerank(row_end, src, 3)
+        g.set_local_values(x3[g2_lo:g2_lo + g2_n])
+        g.iterate(3)
+        y = g.values()
+        err = (np.abs(y - ref6) / np.abs(ref6)).max()
+        report("set_local_values + 3 iterations[%s]" % ename, err <= 1e-6, "max rel err %.2e" % err)
+        g.set_values(x3)
+        g.iterate(3)
+        err = (np.abs(g.values() - ref6) / np.abs(ref6)).max()
+        report("set_values + 3 iterations[%s]" % ename, err <= 1e-6, "max rel err %.2e" % err)
         g.close()
         dist.barrier()
+    os.environ["LUXB_SB"] = "0"
 
     # from host CSC arrays too (every rank passes the whole graph, keeps its slice)
     g = L.LuxGraph.from_csc(row_end, src, app=L.APP_PAGERANK, rank=rank, nranks=world, device=local)

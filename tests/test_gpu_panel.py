@@ -1,7 +1,10 @@
-"""GPU parity of the source-blocked PageRank sweep (panel.cuh: hub destinations x hot source blocks gathered from
-shared memory, the rest through L1, fp64 combine) against the CPU oracle, 1e-6 relative.  The split is normally
-enabled only on large partitions; LUXB_SB=1 with small blocks / thresholds forces it on small graphs so that every
-code path (many blocks, padding vertices, hubs spanning tiles in both CSCs, edge-less hubs in a block) is exercised."""
+"""GPU parity of the PageRank sweep variants against the CPU oracle, 1e-6 relative:
+  * the flagged segmented-scan sweep (seg.cuh) in all its shapes — the default for every PageRank test;
+  * its source-blocked split (panel.cuh: hub destinations x hot source blocks gathered from shared memory, the rest
+    through L1, fp64 combine).  The split is normally enabled only on large partitions; LUXB_SB=1 with small blocks /
+    thresholds forces it on small graphs so that every code path (many blocks, padding, hubs spanning pieces in both
+    streams, (block, hub) pairs without edges, hubs whose edges all moved to the panel) is exercised;
+  * the merge-path tiles of pull.cuh (LUXB_SWEEP=merge), which CC / SSSP pull sweeps keep using."""
 import numpy as np
 import pytest
 
@@ -20,12 +23,13 @@ def assert_close(gpu, ref):
     assert bad.size == 0, "max rel err %.3e at %d (%d bad)" % ((err / np.maximum(np.abs(ref64), 1e-300)).max(), bad[0], bad.size)
 
 
-def force(monkeypatch, bs, min_indeg, blocks=48, shape=0):
+def force(monkeypatch, bs, min_indeg, blocks=48, shape=0, main_shape=0):
     monkeypatch.setenv("LUXB_SB", "1")
     monkeypatch.setenv("LUXB_SB_BS", str(bs))
     monkeypatch.setenv("LUXB_SB_MIN_INDEG", str(min_indeg))
     monkeypatch.setenv("LUXB_SB_BLOCKS", str(blocks))
-    monkeypatch.setenv("LUXB_SB_SHAPE", str(shape))
+    monkeypatch.setenv("LUXB_SEG_PANEL_SHAPE", str(shape))
+    monkeypatch.setenv("LUXB_SEG_MAIN_SHAPE", str(main_shape))
 
 
 @pytest.mark.parametrize("name", sorted(ALL_SMALL))
@@ -36,9 +40,10 @@ def test_panel_small_graphs(name, monkeypatch):
         assert_close(L.pagerank(row_end, src, num_iter=ni), O.pagerank(row_end, src, ni))
 
 
-@pytest.mark.parametrize("bs,min_indeg,blocks,shape", [(64, 4, 48, 0), (256, 16, 8, 1), (1024, 2, 64, 2), (4096, 64, 3, 3), (128, 1, 64, 4)])
-def test_panel_rmat16_parameter_sweep(bs, min_indeg, blocks, shape, monkeypatch):
-    force(monkeypatch, bs, min_indeg, blocks, shape)
+@pytest.mark.parametrize("bs,min_indeg,blocks,shape,main_shape", [(64, 4, 48, 0, 0), (256, 16, 8, 1, 1), (1024, 2, 64, 2, 2), (4096, 64, 3, 3, 3),
+                                                                 (128, 1, 64, 4, 4), (32768, 8, 2, 5, 5)])
+def test_panel_rmat16_parameter_sweep(bs, min_indeg, blocks, shape, main_shape, monkeypatch):
+    force(monkeypatch, bs, min_indeg, blocks, shape, main_shape)
     row_end, src = rmat(16)
     with L.LuxGraph.from_csc(row_end, src) as g:
         g.init()
@@ -92,3 +97,36 @@ def test_panel_set_values_restart(monkeypatch):
         g.set_values(x2)
         g.iterate(3)
         assert np.array_equal(g.values(), x5)
+
+
+@pytest.mark.parametrize("main_shape", [0, 1, 2, 3, 4, 5])
+def test_plain_seg_sweep_shapes(main_shape, monkeypatch):
+    """The flagged stream without the split, every shape, on graphs with hubs spanning many pieces, empty vertices, no edges."""
+    monkeypatch.setenv("LUXB_SB", "0")
+    monkeypatch.setenv("LUXB_SEG_MAIN_SHAPE", str(main_shape))
+    for name in ("star", "trailing_isolated", "no_edges", "rmat12_ragged_nv"):
+        row_end, src = ALL_SMALL[name]()
+        assert_close(L.pagerank(row_end, src, num_iter=3), O.pagerank(row_end, src, 3))
+    row_end, src = rmat(17)
+    assert_close(L.pagerank(row_end, src, num_iter=5), O.pagerank(row_end, src, 5))
+
+
+def test_merge_path_sweep_still_available(monkeypatch):
+    monkeypatch.setenv("LUXB_SWEEP", "merge")
+    row_end, src = rmat(16)
+    assert_close(L.pagerank(row_end, src, num_iter=5), O.pagerank(row_end, src, 5))
+
+
+def test_local_values_roundtrip(monkeypatch):
+    force(monkeypatch, 64, 4)
+    row_end, src = rmat(14)
+    with L.LuxGraph.from_csc(row_end, src) as g:
+        g.init()
+        g.iterate(2)
+        x2 = g.local_values()
+        assert np.array_equal(x2, g.values())  # one rank: the slice is everything
+        g.iterate(3)
+        x5 = g.values()
+        g.set_local_values(x2)
+        g.iterate(3)
+        assert np.array_equal(g.local_values(), x5)
