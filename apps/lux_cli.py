@@ -4,6 +4,7 @@
   python apps/lux_cli.py components -ng 2 -file g.lux [-check] [-verbose]          # components/components.cc:145-175
   python apps/lux_cli.py sssp       -ng 1 -file g.lux -start 0 [-check]            # sssp/sssp.cc
   python apps/lux_cli.py colfilter  -ng 1 -ni 10 -file ratings.lux                 # col_filter/colfilter.cc:85-107
+  python apps/lux_cli.py converter  -nv N -ne M -input edges.txt -output g.lux     # tools/converter.cc:13-39 (host only)
 
 `-ll:gpu N` is accepted as a synonym of `-ng N` (README.md:47); -ll:fsize / -ll:zsize are accepted and ignored (HBM is
 managed by the library).  With -ng > 1 the driver re-launches itself under torch.distributed.run, one rank per GPU.
@@ -71,7 +72,33 @@ def memory_setting(app, nv, ne, bounds, frontier_bytes):
     return max_fb // 1024 // 1024 + 1, zc // 1024 // 1024 + 1
 
 
+def converter(argv):
+    """tools/converter.cc: same flags, same first stdout line; the conversion itself is luxb_convert_edgelist."""
+    nv, ne, inp, out = 0, 0, "", ""
+    i = 0
+    while i < len(argv):
+        if argv[i] == "-nv":
+            nv = int(argv[i + 1]); i += 1
+        elif argv[i] == "-ne":
+            ne = int(argv[i + 1]); i += 1
+        elif argv[i] == "-input":
+            inp = argv[i + 1]; i += 1
+        elif argv[i] == "-output":
+            out = argv[i + 1]; i += 1
+        i += 1
+    print("nv = %d ne = %d input = %s output = %s" % (nv, ne, inp, out), flush=True)  # converter.cc:80
+    import lux_b200 as L
+    try:
+        L.convert_edgelist(inp, out, nv, ne)
+    except L.LuxError as e:
+        print("converter: %s" % e, file=sys.stderr)
+        return 1
+    return 0
+
+
 def main():
+    if len(sys.argv) >= 2 and sys.argv[1] == "converter":
+        return converter(sys.argv[2:])
     if len(sys.argv) < 2 or sys.argv[1] not in APPS:
         print(__doc__)
         return 2

@@ -101,6 +101,15 @@ int luxb_open_rmat(int scale, luxb_vid nv, luxb_eid ne, uint64_t seed, const lux
 int luxb_open_bipartite(luxb_vid users, luxb_vid items, luxb_eid ratings, uint64_t seed, const luxb_config* cfg,
                         luxb_graph** out);
 
+/* ---- .lux files (tools/converter.cc; format README.md:75, graph.h:32) — host only ---------------------------------- */
+/* Write a CSC as a .lux file: u32 nv, u64 ne, u64 row_end[nv], u32 src[ne], then i32 weight[ne] when csc->weight is set
+ * (what EDGE_WEIGHT apps read, pull_model.inl:309-317) or else u32 out_degree[nv] (what converter.cc:124 appends). */
+int luxb_write_lux(const char* lux_path, const luxb_csc* csc);
+/* = tools/converter.cc main (-nv -ne -input -output): text edge list "src dst" per edge -> .lux.  Edges are put in
+ * canonical (dst, src) order (the reference's std::sort by dst leaves the order inside a destination unspecified);
+ * malformed input is an error code, not an assert. */
+int luxb_convert_edgelist(const char* edge_list_path, const char* lux_path, luxb_vid nv, luxb_eid ne);
+
 /* ---- partition table (Graph::rowLeft/rowRight/fqLeft/fqRight, core/graph.h:62-63) ------------------------ */
 int luxb_graph_info(const luxb_graph* g, luxb_vid* nv, luxb_eid* ne, int* nranks);
 /* nranks entries each; fq_* are the frontier-slot byte ranges of push_model.inl:393-397 (NULL to skip). */
@@ -202,6 +211,8 @@ int luxb_get_local_csc(luxb_graph* g, luxb_eid* row_end_abs, luxb_vid* src, int3
 void luxb_close(luxb_graph* g);
 const char* luxb_last_error(void);
 const char* luxb_version(void);
+/* Incremented whenever the layout of a public struct changes; bindings check it before the first call. */
+int luxb_abi_version(void);
 
 #ifdef __cplusplus
 }

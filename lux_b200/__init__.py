@@ -6,9 +6,9 @@ graph without the library or without a GPU raises.
 """
 from .binding import (APP_PAGERANK, APP_CC, APP_SSSP, APP_COLFILTER, EXCHANGE_NCCL, EXCHANGE_P2P, EXCHANGE_P2P_FUSED, DENSE_BITMAP,
                       SPARSE_QUEUE, CF_K, LuxError, LuxGraph, load_library, partition_csc, library_path,
-                      declared_symbols)
+                      declared_symbols, write_lux, convert_edgelist)
 from .apps import pagerank, components, sssp, colfilter  # noqa: F401
 
 __all__ = ["APP_PAGERANK", "APP_CC", "APP_SSSP", "APP_COLFILTER", "EXCHANGE_NCCL", "EXCHANGE_P2P", "EXCHANGE_P2P_FUSED", "DENSE_BITMAP",
            "SPARSE_QUEUE", "CF_K", "LuxError", "LuxGraph", "load_library", "partition_csc", "library_path",
-           "declared_symbols", "pagerank", "components", "sssp", "colfilter"]
+           "declared_symbols", "write_lux", "convert_edgelist", "pagerank", "components", "sssp", "colfilter"]

@@ -55,8 +55,12 @@ def declared_symbols():
     return sorted(set(re.findall(r"\b(luxb_[a-z0-9_]+)\s*\(", text)))
 
 
+ABI_VERSION = 2  # must equal luxb_abi_version(): layout of luxb_config / luxb_stats_t / luxb_device_view
+
+
 def load_library():
-    """Load libluxb.so, building it in-tree if needed.  Raises (never falls back) if that is impossible."""
+    """Load libluxb.so, building it in-tree if its sources are newer.  Raises (never falls back): a library that is
+    missing, stale and not rebuildable, or built from another revision of the ABI is an error."""
     global _lib
     if _lib is not None:
         return _lib
@@ -65,12 +69,14 @@ def load_library():
         try:
             _build.build()
         except Exception as e:  # noqa: BLE001
-            if not os.path.exists(path):
-                raise LuxError("libluxb.so is missing and could not be built (%s); lux_b200 has no CPU fallback" % e)
+            raise LuxError("libluxb.so is %s and could not be built (%s); lux_b200 has no CPU fallback" % (
+                "stale" if os.path.exists(path) else "missing", e))
     L = C.CDLL(path)
     L.luxb_last_error.restype = C.c_char_p
     L.luxb_version.restype = C.c_char_p
     L.luxb_close.restype = None
+    if not hasattr(L, "luxb_abi_version") or L.luxb_abi_version() != ABI_VERSION:
+        raise LuxError("libluxb.so at %s was built for another ABI revision than this binding (%d)" % (path, ABI_VERSION))
     _lib = L
     return L
 
@@ -92,6 +98,22 @@ def partition_csc(row_end, ne, P):
     cnt = _chk(load_library().luxb_partition_csc(C.c_uint32(len(row_end)), C.c_uint64(ne), _p(row_end), C.c_int(P),
                                                  _p(rl), _p(rr), _p(cl)), "luxb_partition_csc")
     return cnt, rl, rr, cl
+
+
+def write_lux(path, row_end, src, weight=None):
+    """CSC arrays -> .lux file (tools/converter.cc layout); host only."""
+    row_end = np.ascontiguousarray(row_end, np.uint64)
+    src = np.ascontiguousarray(src, np.uint32)
+    if weight is not None:
+        weight = np.ascontiguousarray(weight, np.int32)
+    csc = _Csc(len(row_end), len(src), _p(row_end), _p(src) if len(src) else None, _p(weight))
+    _chk(load_library().luxb_write_lux(path.encode(), C.byref(csc)), "luxb_write_lux")
+
+
+def convert_edgelist(edge_list_path, lux_path, nv, ne):
+    """Text edge list ("src dst" per line) -> .lux, like tools/converter.cc -nv -ne -input -output; host only."""
+    _chk(load_library().luxb_convert_edgelist(edge_list_path.encode(), lux_path.encode(), C.c_uint32(nv), C.c_uint64(ne)),
+         "luxb_convert_edgelist")
 
 
 _VDTYPE = {APP_PAGERANK: np.float32, APP_CC: np.uint32, APP_SSSP: np.uint32, APP_COLFILTER: np.float32}

@@ -1,4 +1,5 @@
 """In-tree build of libluxb.so (hand-written sm_100a CUDA + the C ABI).  nvcc cross-compiles without a GPU."""
+import fcntl
 import os
 import subprocess
 
@@ -23,13 +24,28 @@ def is_stale():
 
 
 def build(force=False, verbose=False):
-    """Compile lux_b200/csrc/api.cu (which includes every kernel header) into lux_b200/_lib/libluxb.so."""
+    """Compile lux_b200/csrc/api.cu (which includes every kernel header) into lux_b200/_lib/libluxb.so.
+    Safe under torch.distributed.run: ranks serialise on a file lock, only the first one to get it compiles (to a
+    temporary file that is renamed into place, so nobody ever dlopens a half-written library)."""
     if not force and not is_stale():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
-    nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "api.cu"), "-ldl"]
-    subprocess.check_call(cmd, cwd=CSRC)
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():  # another rank built it while we waited
+                return LIB
+            nvcc = os.environ.get("NVCC", "nvcc")
+            tmp = LIB + ".tmp.%d" % os.getpid()
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp, os.path.join(CSRC, "api.cu"), "-ldl"]
+            try:
+                subprocess.check_call(cmd, cwd=CSRC)
+                os.replace(tmp, LIB)
+            finally:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

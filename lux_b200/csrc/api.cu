@@ -227,6 +227,8 @@ static int finish_layout(luxb_graph* g) {
 
 static int validate_row_end(uint32_t nv, uint64_t ne, const uint64_t* row_end) {
   LUXB_ARG(nv >= 1, "graph has no vertices");
+  // device-wide scans / sorts index vertices with 32-bit signed counts and INF = nv must stay a valid label
+  LUXB_ARG(nv < 0x7FFFFFFEu, "nv = %u: at most 2^31 - 2 vertices are supported", nv);
   for (uint32_t v = 1; v < nv; ++v)
     LUXB_ARG(row_end[v] >= row_end[v - 1], "row_end not non-decreasing at vertex %u (pull_model.inl:100-101)", v);
   LUXB_ARG(row_end[nv - 1] == ne, "row_end[nv-1] (%llu) != ne (%llu) (pull_model.inl:102)",
@@ -247,14 +249,21 @@ static int upload_slice(luxb_graph* g, const uint64_t* row_end_slice_abs, const 
                                                                                         g->d_row_end);
   LUXB_CUDA(cudaGetLastError());
   LUXB_CUDA(cudaMemsetAsync(g->d_src, 0, (g->e_part + 8) * 4, g->stream));
-  if (g->e_part) LUXB_CUDA(cudaMemcpyAsync(g->d_src, src_slice, g->e_part * 4, cudaMemcpyHostToDevice, g->stream));
+  if (g->e_part) LUXB_CUDA(cudaMemcpyAsync(g->d_src, src_slice, g->e_part * 4, cudaMemcpyDefault, g->stream));
   if (g->weighted) {
     LUXB_TRY(edge_alloc(g, &g->d_weight, g->e_part + 8));
     LUXB_CUDA(cudaMemsetAsync(g->d_weight, 0, (g->e_part + 8) * 4, g->stream));
-    if (g->e_part) LUXB_CUDA(cudaMemcpyAsync(g->d_weight, weight_slice, g->e_part * 4, cudaMemcpyHostToDevice, g->stream));
+    if (g->e_part) LUXB_CUDA(cudaMemcpyAsync(g->d_weight, weight_slice, g->e_part * 4, cudaMemcpyDefault, g->stream));
   }
+  // every source id of this rank's slice must be a vertex (checked where the data already is: on the device)
+  unsigned long long* d_bad = reinterpret_cast<unsigned long long*>(d_tmp);
+  LUXB_CUDA(cudaMemsetAsync(d_bad, 0, 8, g->stream));
+  if (g->e_part) src_out_of_range_kernel<<<g->num_sms * 8, 256, 0, g->stream>>>(g->d_src, g->e_part, g->nv, d_bad);
+  unsigned long long bad = 0;
+  LUXB_CUDA(cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, g->stream));
   LUXB_CUDA(cudaStreamSynchronize(g->stream));
   LUXB_CUDA(cudaFree(d_tmp));
+  LUXB_ARG(bad == 0, "%llu source ids of this rank's slice are >= nv (%u)", bad, g->nv);
   return finish_layout(g);
 }
 
@@ -262,7 +271,8 @@ static int upload_slice(luxb_graph* g, const uint64_t* row_end_slice_abs, const 
 extern "C" {
 
 const char* luxb_last_error(void) { return g_err; }
-const char* luxb_version(void) { return "lux_b200 0.1 (sm_100a)"; }
+const char* luxb_version(void) { return "lux_b200 0.2 (sm_100a)"; }
+int luxb_abi_version(void) { return 2; }
 
 int luxb_partition_csc(luxb_vid nv, luxb_eid ne, const luxb_eid* row_end, int P, luxb_vid* row_left, luxb_vid* row_right,
                        luxb_eid* col_left) {
@@ -280,7 +290,6 @@ int luxb_open_csc(const luxb_csc* csc, const luxb_config* cfg, luxb_graph** out)
   LUXB_TRY(check_config(cfg));
   LUXB_ARG(cfg->app != LUXB_COLFILTER || csc->weight, "col_filter needs edge weights (EDGE_WEIGHT, col_filter/app.h:22)");
   LUXB_TRY(validate_row_end(csc->nv, csc->ne, csc->row_end));
-  for (uint64_t e = 0; e < csc->ne; ++e) LUXB_ARG(csc->src[e] < csc->nv, "src[%llu] out of range", (unsigned long long)e);
   luxb_graph* g = nullptr;
   int rc = graph_begin(cfg, &g);
   if (rc) { if (g) luxb_close(g); return rc; }
@@ -330,12 +339,68 @@ int luxb_open_file(const char* path, const luxb_config* cfg, luxb_graph** out) {
          fread(w.data(), 4, g->e_part, f) == g->e_part;
   fclose(f);
   if (!ok) { luxb_close(g); set_error("%s: truncated edge data", path); return LUXB_ERR_IO; }
-  for (uint64_t e = 0; e < g->e_part; ++e)
-    if (src[e] >= nv) { luxb_close(g); set_error("%s: source id out of range", path); return LUXB_ERR_ARG; }
   rc = upload_slice(g, row_end.data() + (g->n_part ? g->row_left : 0), src.data(), g->weighted ? w.data() : nullptr);
   if (rc) { luxb_close(g); return rc; }
   *out = g;
   return 0;
+}
+
+// ---- .lux writer and edge-list converter (tools/converter.cc) — host only, no device needed -----------------------
+int luxb_write_lux(const char* path, const luxb_csc* csc) {
+  LUXB_ARG(path && csc && csc->row_end && (csc->src || csc->ne == 0), "NULL argument");
+  LUXB_TRY(validate_row_end(csc->nv, csc->ne, csc->row_end));
+  std::vector<uint32_t> deg;
+  if (!csc->weight) {  // the trailer the reference converter writes: out-degrees (converter.cc:124)
+    deg.assign(csc->nv, 0);
+    for (uint64_t e = 0; e < csc->ne; ++e) {
+      LUXB_ARG(csc->src[e] < csc->nv, "src[%llu] out of range", (unsigned long long)e);
+      deg[csc->src[e]]++;
+    }
+  }
+  FILE* f = fopen(path, "wb");
+  if (!f) { set_error("cannot create %s", path); return LUXB_ERR_IO; }
+  bool ok = fwrite(&csc->nv, 4, 1, f) == 1 && fwrite(&csc->ne, 8, 1, f) == 1 &&       // converter.cc:108-109
+            fwrite(csc->row_end, 8, csc->nv, f) == csc->nv &&                          // :110
+            (csc->ne == 0 || fwrite(csc->src, 4, csc->ne, f) == csc->ne);              // :112-123
+  if (ok && csc->weight) ok = csc->ne == 0 || fwrite(csc->weight, 4, csc->ne, f) == csc->ne;  // EDGE_WEIGHT apps read i32 weights here
+  if (ok && !csc->weight) ok = fwrite(deg.data(), 4, csc->nv, f) == csc->nv;                  // :124
+  ok = fclose(f) == 0 && ok;
+  if (!ok) { set_error("short write to %s", path); return LUXB_ERR_IO; }
+  return 0;
+}
+
+int luxb_convert_edgelist(const char* edge_list_path, const char* lux_path, luxb_vid nv, luxb_eid ne) {
+  LUXB_ARG(edge_list_path && lux_path, "NULL argument");
+  LUXB_ARG(nv >= 1, "-nv must be positive");
+  FILE* fin = fopen(edge_list_path, "r");
+  if (!fin) { set_error("cannot open %s", edge_list_path); return LUXB_ERR_IO; }
+  std::vector<uint64_t> keys;  // dst << 32 | src: ascending = canonical (dst, src) order (the reference's std::sort by dst
+  keys.reserve(ne);            // leaves the order inside a destination unspecified; ours is deterministic)
+  for (uint64_t e = 0; e < ne; ++e) {
+    long long a = -1, b = -1;
+    if (fscanf(fin, "%lli %lli", &a, &b) != 2) {  // "%i %i" in converter.cc:90: C integer syntax, whitespace separated
+      fclose(fin);
+      set_error("%s: edge %llu of %llu cannot be read", edge_list_path, (unsigned long long)e, (unsigned long long)ne);
+      return LUXB_ERR_IO;
+    }
+    if (a < 0 || b < 0 || (unsigned long long)a >= nv || (unsigned long long)b >= nv) {  // converter.cc:91-92 asserts
+      fclose(fin);
+      set_error("%s: edge %llu (%lld -> %lld) has an endpoint outside [0, %u)", edge_list_path, (unsigned long long)e, a, b, nv);
+      return LUXB_ERR_ARG;
+    }
+    keys.push_back(((uint64_t)b << 32) | (uint64_t)a);
+  }
+  fclose(fin);
+  std::sort(keys.begin(), keys.end());
+  std::vector<uint64_t> row_end(nv);
+  std::vector<uint32_t> src(ne ? ne : 1);
+  uint64_t cnt = 0;
+  for (uint32_t v = 0; v < nv; ++v) {
+    while (cnt < ne && (uint32_t)(keys[cnt] >> 32) == v) { src[cnt] = (uint32_t)keys[cnt]; ++cnt; }
+    row_end[v] = cnt;  // END offset of v's in-edge block (converter.cc:100-106)
+  }
+  luxb_csc csc{nv, ne, row_end.data(), src.data(), nullptr};
+  return luxb_write_lux(lux_path, &csc);
 }
 
 static int open_generated(const GenSpec& spec, const luxb_config* cfg, luxb_graph** out) {
@@ -447,6 +512,7 @@ int luxb_open_bipartite(luxb_vid users, luxb_vid items, luxb_eid ratings, uint64
                         luxb_graph** out) {
   LUXB_TRY(check_config(cfg));
   LUXB_ARG(users >= 1 && items >= 1, "users and items must be positive");
+  LUXB_ARG((uint64_t)users + items < 0x7FFFFFFEull, "users + items must stay below 2^31 - 2");
   GenSpec s{};
   s.kind = 1; s.nv = users + items; s.ne = 2 * ratings; s.seed = seed; s.users = users; s.items = items;
   return open_generated(s, cfg, out);

@@ -171,6 +171,13 @@ __global__ void rowend_rel_kernel(const uint64_t* __restrict__ row_end_global, u
     rel[i] = i < n_part ? row_end_global[row_left + i] - col_left : ~0ull;
 }
 
+// input validation on the device: number of source ids >= nv in this rank's slice
+__global__ void src_out_of_range_kernel(const uint32_t* __restrict__ src, uint64_t n, uint32_t nv, unsigned long long* __restrict__ bad) {
+  unsigned long long c = 0;
+  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) c += src[e] >= nv;
+  if (c) atomicAdd(bad, c);
+}
+
 __global__ void hist_src_kernel(const uint32_t* __restrict__ src, uint64_t n, uint32_t* __restrict__ cnt) {
   for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x)
     atomicAdd(cnt + src[e], 1u);

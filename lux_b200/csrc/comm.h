@@ -7,6 +7,7 @@
 #include <dlfcn.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <mutex>
 
 namespace luxb {
 
@@ -29,9 +30,11 @@ struct NcclApi {
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 
-  // returns nullptr on success, else a message
+  // returns nullptr on success, else a message.  Thread-safe: one host thread per GPU may race here.
   const char* load() {
-    if (handle) return nullptr;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (handle && GetErrorString) return nullptr;
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char* n : names) {
       handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);

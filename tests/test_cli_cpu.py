@@ -30,3 +30,21 @@ def test_memory_setting_formulas():
     fb, zc = cli.memory_setting("components", nv, ne, b, F)
     assert fb == (ne * 8 + ne * 4 + nv * 8 + nv * 8 + nv * 8 + nv * 4 + 2 * F) // MB + 1
     assert zc == (ne * 4 + nv * 8 + nv * 8 + 2 * F + nv * 8 + ne * 4) // MB + 1
+
+
+def test_converter_tool_runs_without_a_gpu(tmp_path):
+    """`lux_cli.py converter` = tools/converter.cc (flags -nv -ne -input -output, first stdout line) on the product's
+    host-only luxb_convert_edgelist; the file it writes loads through the oracle's reader."""
+    import subprocess
+    import sys
+    import oracle as O
+    edges = [(0, 1), (1, 2), (2, 0), (3, 0), (0, 2)]
+    txt = tmp_path / "e.txt"
+    txt.write_text("".join("%d %d\n" % e for e in edges))
+    out = str(tmp_path / "g.lux")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "apps", "lux_cli.py"), "converter", "-nv", "4", "-ne", "5", "-input", str(txt),
+                        "-output", out], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert p.stdout.startswith("nv = 4 ne = 5 input = %s output = %s" % (txt, out))
+    row_end, src = O.lux_read(out)
+    assert row_end.tolist() == [2, 3, 5, 5] and src.tolist() == [2, 3, 0, 0, 1]
