@@ -1176,12 +1176,14 @@ static int launch_pull(luxb_graph* g, const PullLayout& L, const typename Prog::
 #define LUXB_DECL_MSHAPE(id, warps, stages, rounds) using SegMain##id = SegShape<warps, stages, rounds, false, 0>;
 LUXB_SEG_MAIN_SHAPES(LUXB_DECL_MSHAPE)
 // panel shapes: + shared-memory table capacity (values, <= 32768: 15-bit offsets); one CTA per SM
-#define LUXB_SEG_PANEL_SHAPES(X) X(0, 16, 2, 4, 32768) X(1, 24, 2, 2, 32768) X(2, 31, 2, 2, 32768) X(3, 16, 2, 2, 32768) X(4, 24, 2, 4, 24576) X(5, 31, 2, 1, 32768)
-#define LUXB_DECL_PSHAPE(id, warps, stages, rounds, tab) using SegPanel##id = SegShape<warps, stages, rounds, true, tab>;
+// (..., edges per lane and round)
+#define LUXB_SEG_PANEL_SHAPES(X) \
+  X(0, 31, 2, 2, 32768, 8) X(1, 24, 2, 1, 32768, 16) X(2, 16, 2, 2, 32768, 16) X(3, 24, 2, 2, 32768, 8) X(4, 20, 2, 1, 32768, 16) X(5, 16, 2, 4, 32768, 8)
+#define LUXB_DECL_PSHAPE(id, warps, stages, rounds, tab, v) using SegPanel##id = SegShape<warps, stages, rounds, true, tab, v>;
 LUXB_SEG_PANEL_SHAPES(LUXB_DECL_PSHAPE)
 struct SegShapeInfo { int piece, stage_edges, tab; };
 #define LUXB_MSHAPE_INFO(id, warps, stages, rounds) {SegMain##id::kPiece, SegMain##id::kStageEdges, 0},
-#define LUXB_PSHAPE_INFO(id, warps, stages, rounds, tab) {SegPanel##id::kPiece, SegPanel##id::kStageEdges, SegPanel##id::kTab},
+#define LUXB_PSHAPE_INFO(id, warps, stages, rounds, tab, v) {SegPanel##id::kPiece, SegPanel##id::kStageEdges, SegPanel##id::kTab},
 static const SegShapeInfo kSegMainInfo[] = {LUXB_SEG_MAIN_SHAPES(LUXB_MSHAPE_INFO)};
 static const SegShapeInfo kSegPanelInfo[] = {LUXB_SEG_PANEL_SHAPES(LUXB_PSHAPE_INFO)};
 static const int kNumSegMain = sizeof(kSegMainInfo) / sizeof(SegShapeInfo);
@@ -1189,7 +1191,7 @@ static const int kNumSegPanel = sizeof(kSegPanelInfo) / sizeof(SegShapeInfo);
 
 static void free_layout(PullLayout& L) {
   void* ptrs[] = {L.d_row_end, L.d_row_end32, L.d_src, L.d_tile_v, L.d_head, L.d_tail, L.d_carry, L.d_carry_flag, L.d_block_agg, L.d_block_flag,
-                  L.d_close, L.d_empty};
+                  L.d_close, L.d_empty, L.d_empty_hub};
   for (void* q : ptrs) if (q) cudaFree(q);
   L = PullLayout();
 }
@@ -1208,7 +1210,7 @@ extern "C++" {
 template <class Word, class In>
 static int build_seg_stream(luxb_graph* g, PullLayout& L, const uint64_t* d_row_end, uint32_t n_vtx, const In* d_ids, uint64_t e_cnt,
                             StreamBlocks& blk, uint32_t stage_edges, uint32_t piece, uint32_t vtx_offset, bool want_empty,
-                            uint32_t* super_end) {
+                            const uint32_t* hub_bits, uint32_t* super_end) {
   const int grid = g->num_sms * 8;
   DevTmp tmp;
   L = PullLayout();
@@ -1274,12 +1276,21 @@ static int build_seg_stream(luxb_graph* g, PullLayout& L, const uint64_t* d_row_
   LUXB_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_cnt, L.d_tile_v, (int)L.n_tiles + 1, g->stream));
   uint32_t heads_counted = 0;
   LUXB_CUDA(cudaMemcpyAsync(&heads_counted, L.d_tile_v + L.n_tiles, 4, cudaMemcpyDeviceToHost, g->stream));
-  // 4. vertices without edges
+  // 4. vertices without edges (hubs among them apart)
+  unsigned int* d_cur2 = nullptr;
   if (want_empty) {
-    L.n_empty = n_vtx - n_seg;
-    LUXB_TRY(dmalloc(&L.d_empty, (uint64_t)L.n_empty + 1));
-    empty_list_kernel<<<grid, 256, 0, g->stream>>>(d_flag, d_rank, n_vtx, L.d_empty);
+    const uint32_t n_e = n_vtx - n_seg;
+    LUXB_TRY(dmalloc(&L.d_empty, (uint64_t)n_e + 1));
+    LUXB_TRY(dmalloc(&L.d_empty_hub, (uint64_t)n_e + 1));
+    LUXB_TRY(tmp.alloc(&d_cur2, 2));
+    LUXB_CUDA(cudaMemsetAsync(d_cur2, 0, 8, g->stream));
+    empty_split_kernel<<<grid, 256, 0, g->stream>>>(d_flag, n_vtx, hub_bits, L.d_empty, L.d_empty_hub, d_cur2);
     LUXB_CUDA(cudaGetLastError());
+    unsigned int h_cur2[2] = {0, 0};
+    LUXB_CUDA(cudaMemcpyAsync(h_cur2, d_cur2, 8, cudaMemcpyDeviceToHost, g->stream));
+    LUXB_CUDA(cudaStreamSynchronize(g->stream));
+    L.n_empty = h_cur2[0];
+    L.n_empty_hub = h_cur2[1];
   }
   LUXB_CUDA(cudaStreamSynchronize(g->stream));
   if ((uint64_t)heads_counted != n_heads) {
@@ -1306,7 +1317,7 @@ static int build_plain_seg_layout(luxb_graph* g) {
   blk.vfirst[0] = 0; blk.vfirst[1] = g->n_part;
   blk.ebase[0] = 0; blk.ebase[1] = g->e_part;
   return build_seg_stream<uint32_t, uint32_t>(g, g->sb_main, g->d_row_end, g->n_part, g->hot_n ? g->d_src_gather : g->d_src, g->e_part, blk,
-                                              (uint32_t)shp.stage_edges, (uint32_t)shp.piece, 0, true, nullptr);
+                                              (uint32_t)shp.stage_edges, (uint32_t)shp.piece, 0, true, nullptr, nullptr);
 }
 
 // Split this partition's (hot-packed) CSC into the panel (hot source block x hub destination, 15-bit offsets, gathered
@@ -1413,7 +1424,7 @@ static int build_panel_layout(luxb_graph* g) {
   tmp.release(d_scan_tmp);
   tmp.release(d_vcount);
   LUXB_TRY((build_seg_stream<uint16_t, uint16_t>(g, g->sb_panel, d_vrow, NV, d_src16, e_cov, pblk, (uint32_t)shp.stage_edges,
-                                                 (uint32_t)shp.piece, 0, false, g->sb_super_end)));
+                                                 (uint32_t)shp.piece, 0, false, nullptr, g->sb_super_end)));
   tmp.release(d_vrow);
   tmp.release(d_src16);
 
@@ -1442,7 +1453,7 @@ static int build_panel_layout(luxb_graph* g) {
   mblk.vfirst[0] = 0; mblk.vfirst[1] = g->n_part;
   mblk.ebase[0] = 0; mblk.ebase[1] = e_main;
   LUXB_TRY((build_seg_stream<uint32_t, uint32_t>(g, g->sb_main, d_main_row, g->n_part, d_main_src, e_main, mblk, (uint32_t)mshp.stage_edges,
-                                                 (uint32_t)mshp.piece, 0, true, nullptr)));
+                                                 (uint32_t)mshp.piece, 0, true, d_hub_bits, nullptr)));
   tmp.release(d_main_row);
   tmp.release(d_main_src);
 
@@ -1509,8 +1520,8 @@ static void fill_seg_args(SegArgs<Prog>& a, const PullLayout& L) {
 }  // extern "C++"
 
 // main (L1) stream of the PageRank sweep: seg kernel + fix-up + vertices without in-edges
-static int launch_seg_main(luxb_graph* g, const PullLayout& L, const float* x_cold, float* out_local, const PageRankProgram::Params& prm,
-                           const uint32_t* hub_bits) {
+static int launch_seg_main(luxb_graph* g, const PullLayout& L, const float* x_cold, float* out_local, int out_buffer,
+                           const PageRankProgram::Params& prm, const uint32_t* hub_bits) {
   SegArgs<PageRankProgram> a{};
   fill_seg_args(a, L);
   a.p.n_part = L.n_vtx;
@@ -1532,11 +1543,18 @@ static int launch_seg_main(luxb_graph* g, const PullLayout& L, const float* x_co
   g->stats.kernel_launches++;
   pt_mark(g, 0);
   LUXB_TRY(launch_fixup(g, a.p, L));
-  if (L.n_empty) {
+  // vertices without in-edges in this stream: update(identity) is a constant for PageRank -> once per value buffer;
+  // hubs among them need a raw zero every iteration (the combine overwrites it)
+  if (L.n_empty && !g->empties_done[out_buffer]) {
     empties_kernel<PageRankProgram><<<grid_for(L.n_empty, 256, g->num_sms * 8), 256, 0, g->stream>>>(a.p, L.d_empty, L.n_empty);
-    LUXB_CUDA(cudaGetLastError());
+    g->empties_done[out_buffer] = true;
     g->stats.kernel_launches++;
   }
+  if (L.n_empty_hub) {
+    empties_kernel<PageRankProgram><<<grid_for(L.n_empty_hub, 256, g->num_sms * 8), 256, 0, g->stream>>>(a.p, L.d_empty_hub, L.n_empty_hub);
+    g->stats.kernel_launches++;
+  }
+  LUXB_CUDA(cudaGetLastError());
   pt_mark(g, 1);
   return 0;
 }
@@ -1558,7 +1576,7 @@ static int pagerank_sweep_seg(luxb_graph* g, const float* x_cold, float* x_new, 
     pa.tile_counter = reinterpret_cast<uint32_t*>(g->d_counters + 4);
     LUXB_CUDA(cudaMemsetAsync(pa.tile_counter, 0, 4, g->stream));
     switch (g->seg_panel_shape) {
-#define LUXB_CASE_PSHAPE(id, warps, stages, rounds, tab) \
+#define LUXB_CASE_PSHAPE(id, warps, stages, rounds, tab, v) \
       case id: LUXB_TRY((launch_seg_shape<PageRankProgram, SegPanel##id>(g, pa, 1))); break;
       LUXB_SEG_PANEL_SHAPES(LUXB_CASE_PSHAPE)
       default: set_error("bad panel shape"); return LUXB_ERR_STATE;
@@ -1568,7 +1586,7 @@ static int pagerank_sweep_seg(luxb_graph* g, const float* x_cold, float* x_new, 
     LUXB_TRY(launch_fixup(g, pa.p, PL));
     pt_mark(g, 1);
   }
-  LUXB_TRY(launch_seg_main(g, g->sb_main, x_cold, x_new + g->row_left, prm, g->sb_on ? g->d_hub_bits : nullptr));
+  LUXB_TRY(launch_seg_main(g, g->sb_main, x_cold, x_new + g->row_left, 1 - g->cur, prm, g->sb_on ? g->d_hub_bits : nullptr));
   LUXB_TRY(kt_end(g));
   if (g->sb_on) {
     CombineArgs<PageRankProgram> ca{};
@@ -1978,6 +1996,7 @@ int luxb_get_local_values(luxb_graph* g, void* host_out, size_t bytes) {
 static int values_installed(luxb_graph* g, bool whole_array) {
   const bool labels = g->cfg.app == LUXB_CC || g->cfg.app == LUXB_SSSP;
   if (g->cfg.app == LUXB_PAGERANK) {
+    g->empties_done[g->cur] = false;  // caller data now sits where the constants of the edge-less vertices were
     LUXB_TRY(pagerank_publish(g, (float*)g->d_val[g->cur]));
     g->replica_stale = !whole_array && g->P > 1;
   } else {

@@ -25,8 +25,10 @@ struct PullLayout {
   uint32_t n_fix_blocks = 0;
   // flagged stream (seg.cuh): d_src holds the words, d_tile_v the heads before each piece, n_tiles the pieces
   uint32_t* d_close = nullptr;      // [1 + heads] vertex completed by each head
-  uint32_t* d_empty = nullptr;      // vertices without edges in this stream
+  uint32_t* d_empty = nullptr;      // vertices without edges in this stream that are not hubs
   uint32_t n_empty = 0;
+  uint32_t* d_empty_hub = nullptr;  // ... that are hubs (all their edges moved to the panel)
+  uint32_t n_empty_hub = 0;
   uint32_t n_stages = 0;
   uint64_t n_words = 0;
 };
@@ -130,6 +132,7 @@ struct luxb_graph {
   uint64_t ag_chunk = 0, hot_chunk = 0;  // equal chunk sizes (elements) of the balanced all-gather
 
   // source-blocked PageRank sweep (panel.cuh): hub destinations x hot source blocks in shared memory
+  bool empties_done[2] = {false, false};  // value buffer k already holds update(identity) at the edge-less vertices
   bool seg_on = false;             // PageRank sweeps the flagged stream(s) of seg.cuh (sb_main [+ sb_panel])
   int seg_main_shape = 0, seg_panel_shape = 0;
   bool sb_on = false;

@@ -9,8 +9,8 @@
 //     vertex" (head flag); the rest is the gather id (31 bits: hot-packed id; panel: 15-bit offset into the block's table);
 //   * close_vtx[j] = the vertex whose in-edge list ENDS where head j begins (one u32 per non-empty vertex instead of
 //     one row_end word per vertex; vertices without in-edges are handled by empties_kernel);
-//   * a warp owns a PIECE of kRounds x 256 consecutive edges; per round each lane loads 8 consecutive words with one or
-//     two 128-bit shared-memory loads, issues its 8 gathers, reduces them serially up to the head flags, and one
+//   * a warp owns a PIECE of kRounds x 32 x kV consecutive edges; per round each lane loads kV (8 or 16) consecutive words
+//     with 128-bit shared-memory loads, issues its kV gathers, reduces them serially up to the head flags, and one
 //     segmented warp-shuffle scan stitches the lanes; completed sums are staged in shared memory and written by a
 //     lane-strided pass (update() + coalesced close_vtx loads).  The running carry across rounds is kept in the
 //     program's wide type (fp64 for PageRank);
@@ -30,7 +30,7 @@ namespace luxb {
 
 constexpr uint32_t kDummyVtx = 0xFFFFFFFFu;
 
-template <int kWarps_, int kStages_, int kRounds_, bool kPanel_, int kTab_>
+template <int kWarps_, int kStages_, int kRounds_, bool kPanel_, int kTab_, int kV_ = 8>
 struct SegShape {
   static constexpr int kWarps = kWarps_;
   static constexpr int kThreads = 32 * (kWarps + 1);
@@ -38,7 +38,8 @@ struct SegShape {
   static constexpr int kRounds = kRounds_;
   static constexpr bool kPanel = kPanel_;
   static constexpr int kTab = kTab_;                      // shared-memory table (values); 0 for the L1 sweep
-  static constexpr int kRound = 256;                      // edges per warp round: 32 lanes x 8 consecutive edges
+  static constexpr int kV = kV_;                          // consecutive edges per lane and round (8 or 16)
+  static constexpr int kRound = 32 * kV;                  // edges per warp round
   static constexpr int kPiece = kRounds * kRound;         // edges per warp piece
   static constexpr int kStageEdges = kWarps * kPiece;     // edges per stage (one TMA bulk copy)
   static constexpr int kWordBytes = kPanel ? 2 : 4;
@@ -49,6 +50,7 @@ struct SegShape {
                                        (2 * kStages + 1) * 8 + (size_t)kStages * kHdrElems * 4 + 16;
   static_assert(!kPanel || (kTab > 0 && kTab <= 32768 && kTab % 4 == 0), "panel offsets are 15 bit");
   static_assert(kStageBytes % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
+  static_assert(kV == 8 || kV == 16, "a lane reads its words with 128-bit loads");
 };
 
 template <class Prog>
@@ -63,11 +65,11 @@ struct SegArgs {
 };
 
 template <class Prog, class Shape>
-__global__ void __launch_bounds__(Shape::kThreads) seg_tile_kernel(const __grid_constant__ SegArgs<Prog> a) {
+__global__ void __launch_bounds__(Shape::kThreads, Shape::kPanel ? 1 : 2) seg_tile_kernel(const __grid_constant__ SegArgs<Prog> a) {
   using Acc = typename Prog::Acc;
   using Vertex = typename Prog::Vertex;
   using Wide = typename Prog::Wide;
-  constexpr int kStages = Shape::kStages, kWarps = Shape::kWarps, kRounds = Shape::kRounds;
+  constexpr int kStages = Shape::kStages, kWarps = Shape::kWarps, kRounds = Shape::kRounds, kV = Shape::kV;
   constexpr bool kPanel = Shape::kPanel;
   static_assert(sizeof(Acc) == 4 && sizeof(Vertex) == 4, "4-byte vertex values");
 
@@ -175,33 +177,40 @@ __global__ void __launch_bounds__(Shape::kThreads) seg_tile_kernel(const __grid_
 
 #pragma unroll 1
     for (int r = 0; r < kRounds; ++r) {
-      // ---- 8 consecutive edge words of this lane ----
-      uint32_t id[8];
+      // ---- kV consecutive edge words of this lane: 128-bit shared-memory loads ----
+      uint32_t id[kV];
       uint32_t fm = 0;  // bit k: word k carries a head flag
       if (kPanel) {
-        const uint4 q = *reinterpret_cast<const uint4*>(P + ((size_t)r * Shape::kRound + lane * 8) * 2);
-        const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+        const uint4* src = reinterpret_cast<const uint4*>(P + ((size_t)r * Shape::kRound + lane * kV) * 2);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          id[2 * k] = w4[k] & 0x7FFFu;
-          id[2 * k + 1] = (w4[k] >> 16) & 0x7FFFu;
-          fm |= ((w4[k] >> 15) & 1u) << (2 * k);
-          fm |= (w4[k] >> 31) << (2 * k + 1);
+        for (int c = 0; c < kV / 8; ++c) {
+          const uint4 q = src[c];
+          const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            id[8 * c + 2 * k] = w4[k] & 0x7FFFu;
+            id[8 * c + 2 * k + 1] = (w4[k] >> 16) & 0x7FFFu;
+            fm |= ((w4[k] >> 15) & 1u) << (8 * c + 2 * k);
+            fm |= (w4[k] >> 31) << (8 * c + 2 * k + 1);
+          }
         }
       } else {
-        const uint4* src = reinterpret_cast<const uint4*>(P + ((size_t)r * Shape::kRound + lane * 8) * 4);
-        const uint4 q0 = src[0], q1 = src[1];
-        const uint32_t w8[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        const uint4* src = reinterpret_cast<const uint4*>(P + ((size_t)r * Shape::kRound + lane * kV) * 4);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          id[k] = w8[k] & 0x7FFFFFFFu;
-          fm |= (w8[k] >> 31) << k;
+        for (int c = 0; c < kV / 4; ++c) {
+          const uint4 q = src[c];
+          const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            id[4 * c + k] = w4[k] & 0x7FFFFFFFu;
+            fm |= (w4[k] >> 31) << (4 * c + k);
+          }
         }
       }
       // ---- gathers (compute()) ----
-      Acc val[8];
+      Acc val[kV];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
+      for (int k = 0; k < kV; ++k) {
         if (kPanel) {
           val[k] = Prog::gather(tab[id[k]]);
         } else {
@@ -226,20 +235,20 @@ __global__ void __launch_bounds__(Shape::kThreads) seg_tile_kernel(const __grid_
       }
       const uint32_t excl = incl - cnt;
       const uint32_t n_round = __shfl_sync(0xffffffffu, incl, 31);
-      // ---- serial reduction up to the head flags ----
-      Acc acc = Prog::identity(), first_val = Prog::identity();
-      uint32_t q = 0;
+      // ---- serial segmented reduction inside the lane (branch-free: selects + one predicated store per word) ----
+      Acc run = Prog::identity(), first_val = Prog::identity();
+      uint32_t h = 0;  // heads met so far in this lane
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        if ((fm >> k) & 1u) {
-          if (q == 0) first_val = acc; else sums[excl + q] = acc;
-          acc = Prog::identity();
-          ++q;
-        }
-        acc = Prog::combine(acc, val[k]);
+      for (int k = 0; k < kV; ++k) {
+        const bool f = (fm >> k) & 1u;
+        const Acc closed = run;                               // what a head at word k completes
+        if (f && h != 0) sums[excl + h] = closed;             // the lane's first completion waits for the scan below
+        first_val = (f && h == 0) ? closed : first_val;
+        run = f ? val[k] : Prog::combine(run, val[k]);
+        h += f ? 1u : 0u;
       }
       // ---- segmented inclusive scan of (has head, trailing partial) across the warp ----
-      Acc sv = acc;
+      Acc sv = run;
       uint32_t sf = cnt ? 1u : 0u;
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
@@ -270,7 +279,10 @@ __global__ void __launch_bounds__(Shape::kThreads) seg_tile_kernel(const __grid_
       for (uint32_t li = lane; li < n_round; li += 32) {
         if (li == 0 && defer_first) continue;  // finished by the fix-up kernels (for piece 0 it is the dummy before head 0)
         const uint32_t v = __ldg(a.p.close_vtx + jbase + n_closed + li);
-        if (v != kDummyVtx) store_vertex<Prog>(a.p, v, sums[li]);
+        if (v != kDummyVtx) {
+          if (kPanel) a.p.out[v] = sums[li];  // raw partial sum of a (block, hub) pair; combine_hub_kernel finishes the hub
+          else store_vertex<Prog>(a.p, v, sums[li]);
+        }
       }
       n_closed += n_round;
       __syncwarp();
@@ -343,13 +355,30 @@ __global__ void piece_heads_kernel(const Word* __restrict__ words, uint32_t n_pi
   }
 }
 
-__global__ void empty_list_kernel(const uint32_t* __restrict__ flag, const uint32_t* __restrict__ segrank, uint32_t n_vtx,
-                                  uint32_t* __restrict__ empty_vtx) {
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vtx; i += (uint64_t)gridDim.x * blockDim.x)
-    if (!flag[i]) empty_vtx[i - segrank[i]] = (uint32_t)i;
+// vertices without edges in the stream, split by the hub bitmap (order inside a list is irrelevant: warp-aggregated append)
+__global__ void empty_split_kernel(const uint32_t* __restrict__ flag, uint32_t n_vtx, const uint32_t* __restrict__ hub_bits,
+                                   uint32_t* __restrict__ plain, uint32_t* __restrict__ hubs, unsigned int* __restrict__ cursors) {
+  const unsigned lane = threadIdx.x & 31;
+  const uint64_t n_round = ((uint64_t)n_vtx + 31) & ~31ull;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += (uint64_t)gridDim.x * blockDim.x) {
+    const bool e = i < n_vtx && !flag[i];
+    const bool hub = e && hub_bits != nullptr && ((hub_bits[i >> 5] >> (i & 31)) & 1u);
+    const unsigned mp = __ballot_sync(0xffffffffu, e && !hub), mh = __ballot_sync(0xffffffffu, hub);
+    unsigned bp = 0, bh = 0;
+    if (lane == 0) {
+      if (mp) bp = atomicAdd(cursors + 0, (unsigned)__popc(mp));
+      if (mh) bh = atomicAdd(cursors + 1, (unsigned)__popc(mh));
+    }
+    bp = __shfl_sync(0xffffffffu, bp, 0);
+    bh = __shfl_sync(0xffffffffu, bh, 0);
+    if (e && !hub) plain[bp + __popc(mp & ((1u << lane) - 1))] = (uint32_t)i;
+    if (hub) hubs[bh + __popc(mh & ((1u << lane) - 1))] = (uint32_t)i;
+  }
 }
 
-// per iteration: vertices without in-edges in the swept stream get update(identity) (raw identity for hubs)
+// vertices without in-edges in the swept stream get update(identity) — a constant when update() ignores the old value
+// (PageRank): written once per value buffer; hubs among them get the raw identity EVERY iteration (combine_hub_kernel
+// overwrites it with the final value)
 template <class Prog>
 __global__ void empties_kernel(const __grid_constant__ PullArgs<Prog> a, const uint32_t* __restrict__ empty_vtx, uint32_t n_empty) {
   for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_empty; k += (uint64_t)gridDim.x * blockDim.x)
