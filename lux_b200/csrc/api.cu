@@ -75,9 +75,7 @@ void set_error(const char* fmt, ...) {
 
 // merge-path shapes <items per lane, consumer warps per CTA, ring stages>; chosen at open time (LUXB_PULL_SHAPE).
 // Shared memory is kept small on purpose: what the ring does not take stays L1, and the gather rate follows L1 size.
-#define LUXB_PULL_SHAPES(X) \
-  X(0, 7, 8, 2) X(1, 9, 8, 2) X(2, 11, 8, 2) X(3, 13, 8, 2) X(4, 15, 8, 2) X(5, 7, 16, 2) X(6, 9, 16, 2) X(7, 11, 16, 2) \
-  X(8, 11, 8, 3) X(9, 5, 16, 2) X(10, 7, 12, 2) X(11, 7, 24, 2)
+#define LUXB_PULL_SHAPES(X) X(0, 7, 8, 2) X(1, 9, 8, 2) X(2, 7, 16, 2)
 #define LUXB_DECL_SHAPE(id, ipt, warps, stages) using PullShape##id = PullShape<ipt, warps, stages>;
 LUXB_PULL_SHAPES(LUXB_DECL_SHAPE)
 #define LUXB_TILE_OF(id, ipt, warps, stages) PullShape##id::kTile,
@@ -570,7 +568,8 @@ int luxb_comm_init(luxb_graph* g, const char id[LUXB_UNIQUE_ID_BYTES]) {
 struct P2PBlob {
   cudaIpcMemHandle_t val[2];  // natural-order replicas (col_filter stores into its peers' replicas)
   cudaIpcMemHandle_t xt[2];   // PageRank: packed transfer arrays
-  int has_val, has_xt;
+  cudaIpcMemHandle_t fq;      // CC / SSSP: frontier slots of every partition (val[0] = label replica)
+  int has_val, has_xt, has_fq;
 };
 
 int luxb_p2p_export(luxb_graph* g, void* blob, size_t* blob_bytes) {
@@ -581,11 +580,12 @@ int luxb_p2p_export(luxb_graph* g, void* blob, size_t* blob_bytes) {
   P2PBlob b;
   memset(&b, 0, sizeof(b));
   LUXB_CUDA(cudaSetDevice(g->cfg.device));
-  if (g->cfg.app == LUXB_COLFILTER) {
+  if (g->cfg.app != LUXB_PAGERANK) {
     for (int k = 0; k < 2; ++k)
       if (g->d_val[k]) LUXB_CUDA(cudaIpcGetMemHandle(&b.val[k], g->d_val[k]));
     b.has_val = 1;
   }
+  if (g->d_fq_all) { LUXB_CUDA(cudaIpcGetMemHandle(&b.fq, g->d_fq_all)); b.has_fq = 1; }
   if (g->packed) {
     for (int k = 0; k < 2; ++k) LUXB_CUDA(cudaIpcGetMemHandle(&b.xt[k], g->d_xt[k]));
     b.has_xt = 1;
@@ -610,12 +610,22 @@ int luxb_p2p_import(luxb_graph* g, const void* all_blobs, size_t blob_bytes_each
         if (g->peer_val[k][p]) { cudaIpcCloseMemHandle(g->peer_val[k][p]); g->peer_val[k][p] = nullptr; }
         if (g->peer_xt[k][p]) { cudaIpcCloseMemHandle(g->peer_xt[k][p]); g->peer_xt[k][p] = nullptr; }
       }
+      if (g->peer_fq[p]) { cudaIpcCloseMemHandle(g->peer_fq[p]); g->peer_fq[p] = nullptr; }
     }
   };
   for (int p = 0; p < g->P; ++p) {
     if (p == g->cfg.rank) {
       for (int k = 0; k < 2; ++k) { g->peer_val[k][p] = g->d_val[k]; g->peer_xt[k][p] = g->d_xt[k]; }
+      g->peer_fq[p] = g->d_fq_all;
       continue;
+    }
+    if (blobs[p].has_fq && g->d_fq_all) {
+      cudaError_t e = cudaIpcOpenMemHandle(&g->peer_fq[p], blobs[p].fq, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        set_error("cudaIpcOpenMemHandle (rank %d's frontier slots): %s", p, cudaGetErrorString(e));
+        undo();
+        return LUXB_ERR_CUDA;
+      }
     }
     for (int k = 0; k < 2; ++k) {
       cudaError_t e = cudaSuccess;
@@ -647,6 +657,7 @@ static void p2p_unmap(luxb_graph* g) {
       if (g->peer_val[k][p]) { cudaIpcCloseMemHandle(g->peer_val[k][p]); g->peer_val[k][p] = nullptr; }
       if (g->peer_xt[k][p]) { cudaIpcCloseMemHandle(g->peer_xt[k][p]); g->peer_xt[k][p] = nullptr; }
     }
+    if (g->peer_fq[p]) { cudaIpcCloseMemHandle(g->peer_fq[p]); g->peer_fq[p] = nullptr; }
   }
   g->p2p_ready = false;
 }
@@ -916,7 +927,7 @@ static int build_hot_layout(luxb_graph* g, bool compact_cold) {
 }
 
 static int allgather_slices(luxb_graph* g, void* replica, size_t elem_bytes);
-static int build_pagerank_sweep(luxb_graph* g);
+static int build_seg_sweep(luxb_graph* g);
 static int pagerank_publish(luxb_graph* g, float* x_new);
 
 int luxb_init(luxb_graph* g) {
@@ -934,7 +945,7 @@ int luxb_init(luxb_graph* g) {
       LUXB_CUDA(cudaGetLastError());
       if (g->P > 1) LUXB_NCCL(nccl().AllReduce(g->d_deg, g->d_deg, g->nv, ncclUint32, ncclSum, g->comm, g->stream));
       LUXB_TRY(build_hot_layout(g, /*compact_cold=*/true));
-      LUXB_TRY(build_pagerank_sweep(g));
+      LUXB_TRY(build_seg_sweep(g));
       for (int k = 0; k < 2; ++k) LUXB_TRY(dmalloc((float**)&g->d_val[k], (uint64_t)g->nv + 64));
       pr_init_kernel<<<grid, 256, 0, g->stream>>>(g->d_deg, g->nv, (float*)g->d_val[0]);
       LUXB_CUDA(cudaMemsetAsync(g->d_val[1], 0, (size_t)g->nv * 4, g->stream));
@@ -997,8 +1008,10 @@ int luxb_init(luxb_graph* g) {
         LUXB_CUDA(cudaGetLastError());
         if (g->P > 1) LUXB_NCCL(nccl().AllReduce(g->d_deg, g->d_deg, g->nv, ncclUint32, ncclSum, g->comm, g->stream));
         LUXB_TRY(build_hot_layout(g, /*compact_cold=*/false));
+        LUXB_TRY(build_seg_sweep(g));
         if (g->hot_n) {
-          LUXB_TRY(dmalloc((uint32_t**)&g->d_hot, g->hot_n));
+          LUXB_TRY(dmalloc((uint32_t**)&g->d_hot, (uint64_t)g->hot_n + 65536));  // + one table of slack (panel.cuh)
+          LUXB_CUDA(cudaMemsetAsync(g->d_hot, 0, ((size_t)g->hot_n + 65536) * 4, g->stream));
           LUXB_TRY(set_l2_persisting_window(g, g->d_hot, (size_t)g->hot_n * 4));
         }
       }
@@ -1172,7 +1185,7 @@ static int launch_pull(luxb_graph* g, const PullLayout& L, const typename Prog::
 
 // ---- flagged segmented-scan sweep (seg.cuh) and its source-blocked variant (panel.cuh) ------------------------------
 // shapes <consumer warps, ring stages, rounds of 256 edges per warp piece>
-#define LUXB_SEG_MAIN_SHAPES(X) X(0, 8, 2, 2) X(1, 8, 3, 1) X(2, 12, 2, 1) X(3, 8, 2, 4) X(4, 16, 2, 1) X(5, 8, 4, 1)
+#define LUXB_SEG_MAIN_SHAPES(X) X(0, 8, 2, 2) X(1, 8, 3, 1) X(2, 12, 2, 1) X(3, 8, 2, 4) X(4, 16, 2, 1) X(5, 8, 4, 1) X(6, 8, 2, 1) X(7, 6, 2, 2)
 #define LUXB_DECL_MSHAPE(id, warps, stages, rounds) using SegMain##id = SegShape<warps, stages, rounds, false, 0>;
 LUXB_SEG_MAIN_SHAPES(LUXB_DECL_MSHAPE)
 // panel shapes: + shared-memory table capacity (values, <= 32768: 15-bit offsets); one CTA per SM
@@ -1458,8 +1471,9 @@ static int build_panel_layout(luxb_graph* g) {
   tmp.release(d_main_src);
 
   // 6. raw panel sums: one slot per (block, hub); slots of (block, hub) pairs without edges stay 0 forever
+  // (the program's identity: 0 bits for sums and max labels, all ones for min distances)
   LUXB_TRY(dmalloc(&g->d_sb_partial, (uint64_t)NV + 1));
-  LUXB_CUDA(cudaMemsetAsync(g->d_sb_partial, 0, ((size_t)NV + 1) * 4, g->stream));
+  LUXB_CUDA(cudaMemsetAsync(g->d_sb_partial, g->cfg.app == LUXB_SSSP ? 0xFF : 0, ((size_t)NV + 1) * 4, g->stream));
   LUXB_CUDA(cudaStreamSynchronize(g->stream));
   g->d_hub_vtx = d_hub_vtx; tmp.keep(d_hub_vtx);
   g->d_hub_bits = d_hub_bits; tmp.keep(d_hub_bits);
@@ -1478,15 +1492,16 @@ static int build_panel_layout(luxb_graph* g) {
   return 0;
 }
 
-// PageRank's sweep structures: the flagged stream(s) of seg.cuh.  LUXB_SWEEP=merge keeps the merge-path tiles of pull.cuh.
-static int build_pagerank_sweep(luxb_graph* g) {
+// The pull sweep's structures (PageRank; CC / SSSP pull iterations): the flagged stream(s) of seg.cuh.
+// LUXB_SWEEP=merge keeps the merge-path tiles of pull.cuh.
+static int build_seg_sweep(luxb_graph* g) {
   g->seg_on = false;
   g->sb_on = false;
   if (const char* env = getenv("LUXB_SWEEP")) if (!strcmp(env, "merge")) return 0;
   if (g->n_part == 0 || g->cfg.zero_copy_edges || g->e_part >= 0xFFFFFFF0ull) return 0;  // zero-copy graphs keep the canonical arrays
   g->seg_main_shape = env_int("LUXB_SEG_MAIN_SHAPE", 0);
   if (g->seg_main_shape < 0 || g->seg_main_shape >= kNumSegMain) g->seg_main_shape = 0;
-  g->seg_panel_shape = env_int("LUXB_SEG_PANEL_SHAPE", 0);
+  g->seg_panel_shape = env_int("LUXB_SEG_PANEL_SHAPE", 1);
   if (g->seg_panel_shape < 0 || g->seg_panel_shape >= kNumSegPanel) g->seg_panel_shape = 0;
   LUXB_TRY(build_panel_layout(g));
   if (!g->sb_on) {
@@ -1519,15 +1534,20 @@ static void fill_seg_args(SegArgs<Prog>& a, const PullLayout& L) {
 }
 }  // extern "C++"
 
-// main (L1) stream of the PageRank sweep: seg kernel + fix-up + vertices without in-edges
-static int launch_seg_main(luxb_graph* g, const PullLayout& L, const float* x_cold, float* out_local, int out_buffer,
-                           const PageRankProgram::Params& prm, const uint32_t* hub_bits) {
-  SegArgs<PageRankProgram> a{};
+extern "C++" {
+// main (L1) stream of a pull sweep: seg kernel + fix-up + vertices without in-edges.
+// out_buffer >= 0 (PageRank): index of the value buffer written, for the once-per-buffer constants of edge-less vertices;
+// < 0 (labels): `out_local` already holds the old values, edge-less vertices keep them.
+template <class Prog>
+static int launch_seg_main(luxb_graph* g, const PullLayout& L, const typename Prog::Vertex* x_nat, const typename Prog::Vertex* x_cold,
+                           typename Prog::Vertex* out_local, int out_buffer, const typename Prog::Params& prm, const uint32_t* hub_bits) {
+  SegArgs<Prog> a{};
   fill_seg_args(a, L);
   a.p.n_part = L.n_vtx;
   a.p.row_left = g->row_left;
+  a.p.x_nat = x_nat;
   a.p.x_old = x_cold;
-  a.p.x_hot = (const float*)g->d_hot;
+  a.p.x_hot = reinterpret_cast<const typename Prog::Vertex*>(g->d_hot);
   a.p.hot_n = g->hot_n;
   a.p.out = out_local;
   a.p.prm = prm;
@@ -1536,22 +1556,22 @@ static int launch_seg_main(luxb_graph* g, const PullLayout& L, const float* x_co
   LUXB_CUDA(cudaMemsetAsync(a.tile_counter, 0, 4, g->stream));
   switch (g->seg_main_shape) {
 #define LUXB_CASE_MSHAPE(id, warps, stages, rounds) \
-    case id: LUXB_TRY((launch_seg_shape<PageRankProgram, SegMain##id>(g, a, g->pull_ctas))); break;
+    case id: LUXB_TRY((launch_seg_shape<Prog, SegMain##id>(g, a, g->pull_ctas))); break;
     LUXB_SEG_MAIN_SHAPES(LUXB_CASE_MSHAPE)
     default: set_error("bad seg shape"); return LUXB_ERR_STATE;
   }
   g->stats.kernel_launches++;
   pt_mark(g, 0);
   LUXB_TRY(launch_fixup(g, a.p, L));
-  // vertices without in-edges in this stream: update(identity) is a constant for PageRank -> once per value buffer;
-  // hubs among them need a raw zero every iteration (the combine overwrites it)
-  if (L.n_empty && !g->empties_done[out_buffer]) {
-    empties_kernel<PageRankProgram><<<grid_for(L.n_empty, 256, g->num_sms * 8), 256, 0, g->stream>>>(a.p, L.d_empty, L.n_empty);
+  // vertices without in-edges in this stream.  PageRank: update(identity) is a constant -> written once per value
+  // buffer.  Hubs among them need the raw identity every sweep (the combine overwrites it).
+  if (out_buffer >= 0 && L.n_empty && !g->empties_done[out_buffer]) {
+    empties_kernel<Prog><<<grid_for(L.n_empty, 256, g->num_sms * 8), 256, 0, g->stream>>>(a.p, L.d_empty, L.n_empty);
     g->empties_done[out_buffer] = true;
     g->stats.kernel_launches++;
   }
   if (L.n_empty_hub) {
-    empties_kernel<PageRankProgram><<<grid_for(L.n_empty_hub, 256, g->num_sms * 8), 256, 0, g->stream>>>(a.p, L.d_empty_hub, L.n_empty_hub);
+    empties_kernel<Prog><<<grid_for(L.n_empty_hub, 256, g->num_sms * 8), 256, 0, g->stream>>>(a.p, L.d_empty_hub, L.n_empty_hub);
     g->stats.kernel_launches++;
   }
   LUXB_CUDA(cudaGetLastError());
@@ -1559,15 +1579,18 @@ static int launch_seg_main(luxb_graph* g, const PullLayout& L, const float* x_co
   return 0;
 }
 
-// one PageRank sweep = [panel stream (shared-memory gathers) +] main stream (L1 gathers) [+ hub combine]
-static int pagerank_sweep_seg(luxb_graph* g, const float* x_cold, float* x_new, const PageRankProgram::Params& prm) {
+// one pull sweep = [panel stream (shared-memory gathers) +] main stream (L1 gathers) [+ hub combine]
+template <class Prog>
+static int sweep_seg(luxb_graph* g, const typename Prog::Vertex* x_nat, const typename Prog::Vertex* x_cold, typename Prog::Vertex* out_local,
+                     int out_buffer, const typename Prog::Params& prm) {
+  using Acc = typename Prog::Acc;
   LUXB_TRY(kt_begin(g));
   if (g->sb_on) {
     const PullLayout& PL = g->sb_panel;
-    SegArgs<PageRankProgram> pa{};
+    SegArgs<Prog> pa{};
     fill_seg_args(pa, PL);
-    pa.p.x_hot = (const float*)g->d_hot;
-    pa.p.out = g->d_sb_partial;
+    pa.p.x_hot = reinterpret_cast<const typename Prog::Vertex*>(g->d_hot);
+    pa.p.out = reinterpret_cast<typename Prog::Vertex*>(g->d_sb_partial);
     pa.p.raw_out = 1;
     pa.p.prm = prm;
     pa.bs = g->sb_bs;
@@ -1577,7 +1600,7 @@ static int pagerank_sweep_seg(luxb_graph* g, const float* x_cold, float* x_new, 
     LUXB_CUDA(cudaMemsetAsync(pa.tile_counter, 0, 4, g->stream));
     switch (g->seg_panel_shape) {
 #define LUXB_CASE_PSHAPE(id, warps, stages, rounds, tab, v) \
-      case id: LUXB_TRY((launch_seg_shape<PageRankProgram, SegPanel##id>(g, pa, 1))); break;
+      case id: LUXB_TRY((launch_seg_shape<Prog, SegPanel##id>(g, pa, 1))); break;
       LUXB_SEG_PANEL_SHAPES(LUXB_CASE_PSHAPE)
       default: set_error("bad panel shape"); return LUXB_ERR_STATE;
     }
@@ -1586,26 +1609,28 @@ static int pagerank_sweep_seg(luxb_graph* g, const float* x_cold, float* x_new, 
     LUXB_TRY(launch_fixup(g, pa.p, PL));
     pt_mark(g, 1);
   }
-  LUXB_TRY(launch_seg_main(g, g->sb_main, x_cold, x_new + g->row_left, 1 - g->cur, prm, g->sb_on ? g->d_hub_bits : nullptr));
+  LUXB_TRY((launch_seg_main<Prog>(g, g->sb_main, x_nat, x_cold, out_local, out_buffer, prm, g->sb_on ? g->d_hub_bits : nullptr)));
   LUXB_TRY(kt_end(g));
   if (g->sb_on) {
-    CombineArgs<PageRankProgram> ca{};
+    CombineArgs<Prog> ca{};
     ca.hub_vtx = g->d_hub_vtx;
     ca.n_hub = g->sb_n_hub;
     ca.n_blocks = g->sb_n_blocks;
     ca.row_left = g->row_left;
     ca.pb = g->sb_pb;
-    ca.partial = g->d_sb_partial;
-    ca.out = x_new + g->row_left;
+    ca.partial = reinterpret_cast<const Acc*>(g->d_sb_partial);
+    ca.x_nat = x_nat;
+    ca.out = out_local;
     ca.prm = prm;
     ca.n_peers = 0;
-    combine_hub_kernel<PageRankProgram><<<grid_for(g->sb_n_hub, 256, g->num_sms * 8), 256, 0, g->stream>>>(ca);
+    combine_hub_kernel<Prog><<<grid_for(g->sb_n_hub, 256, g->num_sms * 8), 256, 0, g->stream>>>(ca);
     LUXB_CUDA(cudaGetLastError());
     g->stats.kernel_launches++;
     pt_mark(g, 6);
   }
   return 0;
 }
+}  // extern "C++"
 
 // After a sweep (or luxb_set_values): x_new holds this rank's final slice in natural order.  Make it visible to the
 // next sweep of every rank: refresh the hot copies and, on several ranks, run the PACKED exchange — only vertices that are
@@ -1678,7 +1703,7 @@ static int pagerank_iteration(luxb_graph* g) {
   float* x_new = (float*)g->d_val[1 - g->cur];
   const float* x_cold = g->packed ? g->d_xt[g->cur_xt] + g->hot_n : x_old;
   if (g->seg_on) {
-    LUXB_TRY(pagerank_sweep_seg(g, x_cold, x_new, prm));
+    LUXB_TRY((sweep_seg<PageRankProgram>(g, x_old, x_cold, x_new + g->row_left, 1 - g->cur, prm)));
   } else {
     LUXB_TRY(launch_pull<PageRankProgram>(g, base_layout(g, g->hot_n ? g->d_src_gather : g->d_src), x_old, x_cold, (const float*)g->d_hot,
                                           g->hot_n, x_new + g->row_left, prm));
@@ -1751,8 +1776,12 @@ static int label_iteration(luxb_graph* g) {
       hot_refresh_kernel<uint32_t><<<grid_for(g->hot_n, 256, g->num_sms * 8), 256, 0, g->stream>>>((uint32_t*)g->d_hot, lab, g->d_hot_order, 0, g->hot_n);
       g->stats.kernel_launches++;
     }
-    LUXB_TRY(launch_pull<Prog>(g, base_layout(g, g->hot_n ? g->d_src_gather : g->d_src), lab, lab, (const uint32_t*)g->d_hot, g->hot_n,
-                               g->d_cur, prm));
+    if (g->seg_on) {
+      LUXB_TRY((sweep_seg<Prog>(g, lab, lab, g->d_cur, -1, prm)));
+    } else {
+      LUXB_TRY(launch_pull<Prog>(g, base_layout(g, g->hot_n ? g->d_src_gather : g->d_src), lab, lab, (const uint32_t*)g->d_hot, g->hot_n,
+                                 g->d_cur, prm));
+    }
     g->stats.edges_processed += g->e_part;
     g->stats.pull_iterations++;
   } else if (g->n_part && old_size) {
@@ -1846,7 +1875,45 @@ static int label_iteration(luxb_graph* g) {
   }
   uint64_t total = 0;
   for (int p = 0; p < g->P; ++p) total += g->h_hdr[2 * p + 1];
-  if (g->P > 1) {
+  if (g->P > 1 && g->p2p_ready && g->cfg.exchange != LUXB_EXCHANGE_NCCL) {
+    // Frontier P2P push: this partition's new frontier slot — header + bitmap, or header + (id, label) pairs —
+    // and, for a dense frontier, its label slice are stored straight into EVERY peer's slot table / label replica over
+    // NVLink by one kernel (128-bit stores; disjoint ranges, no atomics across GPUs).  Barrier before: every rank has
+    // finished the kernels that read this iteration's slots and labels; barrier after: all pushes have landed.
+    LUXB_TRY(p2p_barrier(g));
+    PushRegions r{};
+    const uint32_t my_type = g->h_hdr[2 * me], my_cnt = g->h_hdr[2 * me + 1];
+    const size_t slot_off = g->slot_off[me];
+    r.n_peers = 0;
+    for (int p = 0; p < g->P; ++p) {
+      unsigned char* fq_p = reinterpret_cast<unsigned char*>(g->peer_fq[p]);
+      uint32_t* lab_p = reinterpret_cast<uint32_t*>(g->peer_val[0][p]);
+      r.dst[0][r.n_peers] = reinterpret_cast<uint32_t*>(fq_p + slot_off);
+      if (my_type == LUXB_DENSE_BITMAP) r.dst[1][r.n_peers] = lab_p + g->rl[me];
+      else r.dst[1][r.n_peers] = reinterpret_cast<uint32_t*>(fq_p + slot_off + 8 + (size_t)g->cap[me] * 4);
+      r.n_peers++;
+    }
+    r.src[0] = reinterpret_cast<const uint32_t*>(new_slot);
+    r.n_regions = 1;
+    if (my_cnt && g->n_part) {
+      if (my_type == LUXB_DENSE_BITMAP) {
+        r.words[0] = 2 + ((size_t)g->n_part + 31) / 32;
+        r.src[1] = g->d_cur;
+        r.words[1] = g->n_part;
+      } else {
+        r.words[0] = 2 + my_cnt;
+        r.src[1] = reinterpret_cast<const uint32_t*>(new_slot + 8 + (size_t)g->cap[me] * 4);
+        r.words[1] = my_cnt;
+      }
+      r.n_regions = 2;
+    } else {
+      r.words[0] = 2;
+    }
+    p2p_push_kernel<<<g->num_sms * 2, 512, 0, g->stream>>>(r);
+    LUXB_CUDA(cudaGetLastError());
+    g->stats.kernel_launches++;
+    LUXB_TRY(p2p_barrier(g));
+  } else if (g->P > 1) {
     LUXB_NCCL(nccl().GroupStart());
     for (int p = 0; p < g->P; ++p) {
       uint32_t type = g->h_hdr[2 * p], cnt = g->h_hdr[2 * p + 1];

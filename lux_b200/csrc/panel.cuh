@@ -132,7 +132,8 @@ struct CombineArgs {
   const uint32_t* hub_vtx;   // [n_hub] local vertex ids
   uint32_t n_hub, n_blocks, row_left;
   PanelBases pb;
-  const float* partial;      // [NV]
+  const typename Prog::Acc* partial;  // [NV] raw panel reductions
+  const typename Prog::Vertex* x_nat; // natural-order values of the previous iteration (update()'s old value)
   typename Prog::Vertex* out;  // [n_part] local; holds the main kernel's RAW sum for hub vertices on entry
   typename Prog::Params prm;
   int n_peers;
@@ -143,9 +144,12 @@ template <class Prog>
 __global__ void combine_hub_kernel(const __grid_constant__ CombineArgs<Prog> a) {
   for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < a.n_hub; h += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t v = a.hub_vtx[h];
-    typename Prog::Wide t = Prog::widen(a.out[v]);
+    typename Prog::Acc raw0;
+    memcpy(&raw0, &a.out[v], sizeof(raw0));  // the main sweep left its RAW reduction in the value slot
+    typename Prog::Wide t = Prog::widen(raw0);
     for (uint32_t b = 0; b < a.n_blocks; ++b) t = Prog::wcombine(t, Prog::widen(a.partial[a.pb.vbase[b] + h]));
-    const typename Prog::Vertex nv_ = Prog::update(a.row_left + v, Prog::narrow(t), typename Prog::Vertex(), a.prm);
+    const typename Prog::Vertex oldv = Prog::kNeedsOld ? a.x_nat[a.row_left + v] : typename Prog::Vertex();
+    const typename Prog::Vertex nv_ = Prog::update(a.row_left + v, Prog::narrow(t), oldv, a.prm);
     a.out[v] = nv_;
     for (int p = 0; p < a.n_peers; ++p) a.peer_out[p][v] = nv_;
   }

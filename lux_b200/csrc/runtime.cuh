@@ -127,7 +127,7 @@ struct luxb_graph {
   luxb::ncclComm_t comm = nullptr;
   bool p2p_ready = false;
   void* peer_val[2][LUXB_MAX_PARTS]{};  // imported replicas of the peers (P2P exchange)
-  void* peer_hot[LUXB_MAX_PARTS]{};
+  void* peer_fq[LUXB_MAX_PARTS]{};      // imported frontier slot tables of the peers (CC / SSSP P2P push)
   uint32_t* d_sync = nullptr;
   uint64_t ag_chunk = 0, hot_chunk = 0;  // equal chunk sizes (elements) of the balanced all-gather
 
@@ -141,7 +141,7 @@ struct luxb_graph {
   int sb_shape = 0;
   uint32_t* d_hub_vtx = nullptr;
   uint32_t* d_hub_bits = nullptr;
-  float* d_sb_partial = nullptr;   // [NV] raw panel sums
+  uint32_t* d_sb_partial = nullptr;  // [NV] raw panel reductions (4-byte Acc of the app's program)
   luxb::PanelBases sb_pb{};
   uint32_t sb_super_end[luxb::kPanelMaxBlocks]{};
 

@@ -235,17 +235,31 @@ __global__ void __launch_bounds__(Shape::kThreads, Shape::kPanel ? 1 : 2) seg_ti
       }
       const uint32_t excl = incl - cnt;
       const uint32_t n_round = __shfl_sync(0xffffffffu, incl, 31);
-      // ---- serial segmented reduction inside the lane (branch-free: selects + one predicated store per word) ----
+      // ---- serial segmented reduction inside the lane ----
       Acc run = Prog::identity(), first_val = Prog::identity();
       uint32_t h = 0;  // heads met so far in this lane
+      if (kPanel) {
+        // shared-memory gathers: the instruction stream is the bound -> branch-free (selects + one predicated store per word)
 #pragma unroll
-      for (int k = 0; k < kV; ++k) {
-        const bool f = (fm >> k) & 1u;
-        const Acc closed = run;                               // what a head at word k completes
-        if (f && h != 0) sums[excl + h] = closed;             // the lane's first completion waits for the scan below
-        first_val = (f && h == 0) ? closed : first_val;
-        run = f ? val[k] : Prog::combine(run, val[k]);
-        h += f ? 1u : 0u;
+        for (int k = 0; k < kV; ++k) {
+          const bool f = (fm >> k) & 1u;
+          const Acc closed = run;                               // what a head at word k completes
+          if (f && h != 0) sums[excl + h] = closed;             // the lane's first completion waits for the scan below
+          first_val = (f && h == 0) ? closed : first_val;
+          run = f ? val[k] : Prog::combine(run, val[k]);
+          h += f ? 1u : 0u;
+        }
+      } else {
+        // L1 gathers: latency bound, heads are rare (1 in ~8 edges) -> skip the bookkeeping with a branch (measured faster)
+#pragma unroll
+        for (int k = 0; k < kV; ++k) {
+          if ((fm >> k) & 1u) {
+            if (h == 0) first_val = run; else sums[excl + h] = run;
+            run = Prog::identity();
+            ++h;
+          }
+          run = Prog::combine(run, val[k]);
+        }
       }
       // ---- segmented inclusive scan of (has head, trailing partial) across the warp ----
       Acc sv = run;

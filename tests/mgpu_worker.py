@@ -77,20 +77,27 @@ def main():
     g.close()
 
     for app, oapp, name in ((L.APP_CC, O.APP_CC, "cc"), (L.APP_SSSP, O.APP_SSSP, "sssp")):
-        g = L.LuxGraph.from_rmat(scale, nv, ne, seed, app=app, rank=rank, nranks=world, device=local, start=0)
-        g.comm_init_torch()
-        g.init()
-        it = g.run_to_convergence()
-        lab = g.values()
-        bad = torch.tensor([g.check()], dtype=torch.int64, device="cuda")
-        dist.all_reduce(bad)
-        active, pull = g.trace()
         ref = O.label_run(oapp, row_end, src, P=world, start=0)
-        report("%s labels world=%d" % (name, world), np.array_equal(lab, ref["labels"]) and int(bad) == 0)
-        report("%s trace" % name, it == ref["iters"] and np.array_equal(active, ref["active"]) and np.array_equal(pull, ref["pull"]),
-               "iters %d vs %d" % (it, ref["iters"]))
-        g.close()
-        dist.barrier()
+        # frontier exchange by NCCL grouped broadcasts, then by direct P2P pushes into the peers' slot tables and label
+        # replicas; the second pass also forces the source-blocked split in the pull sweeps
+        for exchange, ename, sb in ((L.EXCHANGE_NCCL, "nccl", "0"), (L.EXCHANGE_P2P, "p2p push", "1")):
+            os.environ.update({"LUXB_SB": sb, "LUXB_SB_BS": "64", "LUXB_SB_MIN_INDEG": "4"})
+            g = L.LuxGraph.from_rmat(scale, nv, ne, seed, app=app, rank=rank, nranks=world, device=local, start=0, exchange=exchange)
+            g.comm_init_torch()
+            g.init()
+            if exchange != L.EXCHANGE_NCCL:
+                report("p2p_connect[%s %s]" % (name, ename), g.p2p_connect_torch())
+            it = g.run_to_convergence()
+            lab = g.values()
+            bad = torch.tensor([g.check()], dtype=torch.int64, device="cuda")
+            dist.all_reduce(bad)
+            active, pull = g.trace()
+            report("%s labels [%s] world=%d" % (name, ename, world), np.array_equal(lab, ref["labels"]) and int(bad) == 0)
+            report("%s trace [%s]" % (name, ename), it == ref["iters"] and np.array_equal(active, ref["active"]) and np.array_equal(pull, ref["pull"]),
+                   "iters %d vs %d" % (it, ref["iters"]))
+            g.close()
+            dist.barrier()
+    os.environ["LUXB_SB"] = "0"
 
     # col_filter
     users, items, ratings = 4000, 200, 200000

@@ -99,7 +99,7 @@ def test_panel_set_values_restart(monkeypatch):
         assert np.array_equal(g.values(), x5)
 
 
-@pytest.mark.parametrize("main_shape", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("main_shape", [0, 1, 2, 3, 4, 5, 6, 7])
 def test_plain_seg_sweep_shapes(main_shape, monkeypatch):
     """The flagged stream without the split, every shape, on graphs with hubs spanning many pieces, empty vertices, no edges."""
     monkeypatch.setenv("LUXB_SB", "0")
