@@ -41,8 +41,7 @@ typedef enum {
   LUXB_ERR_IO = -3,       /* file could not be read */
   LUXB_ERR_COMM = -4,     /* NCCL / peer-memory error */
   LUXB_ERR_STATE = -5,    /* call out of order (e.g. iterate before init) */
-  LUXB_ERR_NOMEM = -6,
-  LUXB_ERR_PARTITION = -7 /* reference partitioner cannot produce nranks partitions (pull_model.inl:131) */
+  LUXB_ERR_NOMEM = -6
 } luxb_status;
 
 typedef enum {

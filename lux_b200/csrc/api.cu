@@ -168,6 +168,7 @@ static int graph_begin(const luxb_config* cfg, luxb_graph** out) {
   g->pull_ctas = kDefaultPullCtas;
   if (const char* env = getenv("LUXB_PULL_CTAS")) g->pull_ctas = std::max(1, atoi(env));
   if (const char* env = getenv("LUXB_PHASE_TIMING")) g->pt.on = atoi(env) != 0;
+  if (const char* env = getenv("LUXB_L2_HINTS")) g->l2_hints = atoi(env);
   return 0;
 }
 
@@ -695,10 +696,11 @@ struct DevTmp {
 static int build_push_csr(luxb_graph* g) {
   // CSR-by-source over this partition's own edges (init_push_* kernels, components_gpu.cu:550-607):
   // stable radix sort of (src, dst) pairs by src keeps each source's destinations ascending -> deterministic.
+  DevTmp tmp;  // temporaries are released on every exit path
   LUXB_TRY(dmalloc(&g->d_out_end, g->nv));
   LUXB_TRY(dmalloc(&g->d_out_dst, g->e_part));
   uint32_t* d_cnt = nullptr;
-  LUXB_TRY(dmalloc(&d_cnt, g->nv));
+  LUXB_TRY(tmp.alloc(&d_cnt, g->nv));
   LUXB_CUDA(cudaMemsetAsync(d_cnt, 0, (size_t)g->nv * 4, g->stream));
   const int grid = g->num_sms * 8;
   hist_src_kernel<<<grid, 256, 0, g->stream>>>(g->d_src, g->e_part, d_cnt);
@@ -706,15 +708,15 @@ static int build_push_csr(luxb_graph* g) {
   size_t tmp_bytes = 0;
   LUXB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, g->d_out_end, g->d_out_end, (int)g->nv, g->stream));
   void* d_tmp = nullptr;
-  LUXB_CUDA(cudaMalloc(&d_tmp, tmp_bytes + 256));
+  LUXB_TRY(tmp.alloc((char**)&d_tmp, tmp_bytes + 256));
   LUXB_CUDA(cub::DeviceScan::InclusiveSum(d_tmp, tmp_bytes, g->d_out_end, g->d_out_end, (int)g->nv, g->stream));
   LUXB_CUDA(cudaStreamSynchronize(g->stream));
-  LUXB_CUDA(cudaFree(d_tmp));
-  LUXB_CUDA(cudaFree(d_cnt));
+  tmp.release(d_tmp);
+  tmp.release(d_cnt);
   if (g->e_part == 0) return 0;
   uint32_t *d_dst = nullptr, *d_keys_out = nullptr;
-  LUXB_TRY(dmalloc(&d_dst, g->e_part));
-  LUXB_TRY(dmalloc(&d_keys_out, g->e_part));
+  LUXB_TRY(tmp.alloc(&d_dst, g->e_part));
+  LUXB_TRY(tmp.alloc(&d_keys_out, g->e_part));
   edge_dst_kernel<<<grid, 256, 0, g->stream>>>(g->d_row_end, g->n_part, g->e_part, g->row_left, d_dst);
   LUXB_CUDA(cudaGetLastError());
   int vbits = 1;
@@ -722,13 +724,10 @@ static int build_push_csr(luxb_graph* g) {
   tmp_bytes = 0;
   LUXB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, g->d_src, d_keys_out, d_dst, g->d_out_dst, (long long)g->e_part, 0,
                                             vbits, g->stream));
-  LUXB_CUDA(cudaMalloc(&d_tmp, tmp_bytes + 256));
+  LUXB_TRY(tmp.alloc((char**)&d_tmp, tmp_bytes + 256));
   LUXB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, g->d_src, d_keys_out, d_dst, g->d_out_dst, (long long)g->e_part, 0,
                                             vbits, g->stream));
   LUXB_CUDA(cudaStreamSynchronize(g->stream));
-  LUXB_CUDA(cudaFree(d_tmp));
-  LUXB_CUDA(cudaFree(d_dst));
-  LUXB_CUDA(cudaFree(d_keys_out));
   return 0;
 }
 
@@ -1499,7 +1498,7 @@ static int build_seg_sweep(luxb_graph* g) {
   g->sb_on = false;
   if (const char* env = getenv("LUXB_SWEEP")) if (!strcmp(env, "merge")) return 0;
   if (g->n_part == 0 || g->cfg.zero_copy_edges || g->e_part >= 0xFFFFFFF0ull) return 0;  // zero-copy graphs keep the canonical arrays
-  g->seg_main_shape = env_int("LUXB_SEG_MAIN_SHAPE", 0);
+  g->seg_main_shape = env_int("LUXB_SEG_MAIN_SHAPE", 6);
   if (g->seg_main_shape < 0 || g->seg_main_shape >= kNumSegMain) g->seg_main_shape = 0;
   g->seg_panel_shape = env_int("LUXB_SEG_PANEL_SHAPE", 1);
   if (g->seg_panel_shape < 0 || g->seg_panel_shape >= kNumSegPanel) g->seg_panel_shape = 0;
@@ -1552,6 +1551,7 @@ static int launch_seg_main(luxb_graph* g, const PullLayout& L, const typename Pr
   a.p.out = out_local;
   a.p.prm = prm;
   a.p.hub_bits = hub_bits;
+  a.p.l2_hints = g->l2_hints;
   a.tile_counter = reinterpret_cast<uint32_t*>(g->d_counters + 2);
   LUXB_CUDA(cudaMemsetAsync(a.tile_counter, 0, 4, g->stream));
   switch (g->seg_main_shape) {

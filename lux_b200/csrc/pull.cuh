@@ -73,6 +73,7 @@ struct PullArgs {
   // peer stores) — combine_hub_kernel finishes them; raw_out != 0 does that for every vertex (the panel CSC's fix-up)
   const uint32_t* hub_bits;
   int raw_out;
+  int l2_hints;  // gathers carry L2 eviction policies (hot: evict_last, cold: evict_first)
   // flagged segmented-scan sweep (seg.cuh): tile_v counts HEADS, and head j completes vertex close_vtx[j]
   const uint32_t* close_vtx;
   int n_peers;                                        // P2P exchange: peers' slice pointers (local index)
@@ -134,6 +135,23 @@ __device__ __forceinline__ T gather_load(const T* p, bool hot) {
   (void)hot;
   return __ldg(p);
 #endif
+}
+
+// the same with an L2 eviction policy per load (createpolicy): hot copies evict_last, cold values evict_first — the cold
+// sectors (touched once per sweep) must not displace the hot lines in L2 either
+template <class T>
+__device__ __forceinline__ T gather_load_l2(const T* p, bool hot, uint64_t pol_hot, uint64_t pol_cold) {
+  uint32_t v;
+  if (hot) asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol_hot));
+  else asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol_cold));
+  T r;
+  memcpy(&r, &v, 4);
+  return r;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {

@@ -147,6 +147,7 @@ struct luxb_graph {
 
   // launch configuration resolved once at open time (no getenv / function-static state on the hot path)
   int pull_ctas = 3;
+  int l2_hints = 1;   // LUXB_L2_HINTS: per-gather L2 eviction policies in the L1 sweep (hot evict_last, cold evict_first)
   PhaseTimer pt;
 
   // optional per-launch timing of the dominant kernel

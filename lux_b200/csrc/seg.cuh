@@ -157,6 +157,8 @@ __global__ void __launch_bounds__(Shape::kThreads, Shape::kPanel ? 1 : 2) seg_ti
   // ===== consumer warps =====
   Acc* sums = sums_all + (size_t)warp * Shape::kSumElems;
   uint32_t my_gen = 0;
+  const uint64_t pol_hot = a.p.l2_hints ? l2_policy_evict_last() : l2_policy_evict_normal();
+  const uint64_t pol_cold = a.p.l2_hints ? l2_policy_evict_first() : l2_policy_evict_normal();
   for (uint32_t n = 0;; ++n) {
     const int s = n % kStages;
     mbar_wait(&full[s], (n / kStages) & 1u);
@@ -216,7 +218,7 @@ __global__ void __launch_bounds__(Shape::kThreads, Shape::kPanel ? 1 : 2) seg_ti
         } else {
           const bool hot = id[k] < a.p.hot_n;
           const Vertex* ptr = hot ? a.p.x_hot + id[k] : a.p.x_old + (id[k] - a.p.hot_n);
-          val[k] = Prog::gather(gather_load(ptr, hot));
+          val[k] = Prog::gather(gather_load_l2(ptr, hot, pol_hot, pol_cold));
         }
       }
       if (r == kRounds - 1) {

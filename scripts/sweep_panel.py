@@ -17,7 +17,16 @@ scale = int(sys.argv[1]) if len(sys.argv) > 1 else 27
 cfgs = sys.argv[2].split(",") if len(sys.argv) > 2 else ["merge", "off", "off::::1", "off::::3:2", "0:48:64", "1:48:64", "2:48:64", "1:64:32", "1:32:64"]
 nv, ne = 1 << scale, 16 << scale
 blk = None
+extra_keys = set()
 for c in cfgs:
+    c, _, extra = c.partition("@")          # "...@ENV=VAL;ENV=VAL": extra environment for this configuration
+    for k in extra_keys:
+        os.environ.pop(k, None)
+    for kv in filter(None, extra.split(";")):
+        k, _, v = kv.partition("=")
+        os.environ[k] = v
+        extra_keys.add(k)
+    c_label = c + ("@" + extra if extra else "")
     f = c.split(":")
     for k in ("LUXB_SEG_PANEL_SHAPE", "LUXB_SB_BLOCKS", "LUXB_SB_MIN_INDEG", "LUXB_SB_BS", "LUXB_SEG_MAIN_SHAPE", "LUXB_PULL_CTAS", "LUXB_SWEEP"):
         os.environ.pop(k, None)
@@ -54,6 +63,6 @@ for c in cfgs:
         err = (np.abs(x6[blk["vid"]].astype(np.float64) - ref) / np.abs(ref.astype(np.float64))).max()
         k = (s1["dominant_kernel_seconds"] - s0["dominant_kernel_seconds"]) / 20
         t = (s1["loop_seconds"] - s0["loop_seconds"]) / 20
-        print("cfg %-22s panel %.1f%% of edges, %d hubs x %d blocks | sweep %.3f ms, iter %.3f ms, %.1f GTEPS, frac %.3f | parity %.2e %s" % (
-            c, 100.0 * st["panel_edges"] / ne, st["panel_hubs"], st["panel_blocks"], k * 1e3, t * 1e3, ne / t / 1e9,
+        print("cfg %-40s panel %.1f%% of edges, %d hubs x %d blocks | sweep %.3f ms, iter %.3f ms, %.1f GTEPS, frac %.3f | parity %.2e %s" % (
+            c_label, 100.0 * st["panel_edges"] / ne, st["panel_hubs"], st["panel_blocks"], k * 1e3, t * 1e3, ne / t / 1e9,
             (8 * ne + 16 * nv) / k / 1e9 / 6486.8, err, "OK" if err <= 1e-6 else "FAIL"), flush=True)
