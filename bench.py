@@ -192,6 +192,7 @@ def main():
         # oracle port on all host cores.  Input: the ORACLE's own generator (nothing of the product is loaded here);
         # a step = ITERS_PER_STEP PageRank iterations over a bounded, representative sample of the destination vertices.
         import oracle as O
+        O.set_num_threads(os.cpu_count() or 1)  # torch.distributed.run exports OMP_NUM_THREADS=1 to every rank
         t0 = time.perf_counter()
         _, deg, _, blk = oracle_sample(scale, nv, ne, frac_log2=4)
         desc = blk["desc"]
@@ -374,6 +375,7 @@ def main():
         x_k1 = g.values()
         if rank == 0:
             import oracle as O
+            O.set_num_threads(os.cpu_count() or 1)  # torch.distributed.run exports OMP_NUM_THREADS=1 to every rank
             b = g.bounds()
             cover = [0, nv - 1]
             for p in range(world):

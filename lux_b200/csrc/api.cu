@@ -563,6 +563,22 @@ int luxb_comm_init(luxb_graph* g, const char id[LUXB_UNIQUE_ID_BYTES]) {
   ncclUniqueId uid;
   memcpy(&uid, id, LUXB_UNIQUE_ID_BYTES);
   LUXB_NCCL(nccl().CommInitRank(&g->comm, g->P, uid, g->cfg.rank));
+  // a second communicator for the part of the exchange that overlaps with compute on a second stream (operations on
+  // one communicator execute in issue order): rank 0 draws its id and ships it through the first one
+  ncclUniqueId uid2;
+  memset(&uid2, 0, sizeof(uid2));
+  if (g->cfg.rank == 0) LUXB_NCCL(nccl().GetUniqueId(&uid2));
+  char* d_id = nullptr;
+  LUXB_TRY(dmalloc(&d_id, sizeof(uid2)));
+  LUXB_CUDA(cudaMemcpyAsync(d_id, &uid2, sizeof(uid2), cudaMemcpyHostToDevice, g->stream));
+  LUXB_NCCL(nccl().Broadcast(d_id, d_id, sizeof(uid2), ncclUint8, 0, g->comm, g->stream));
+  LUXB_CUDA(cudaMemcpyAsync(&uid2, d_id, sizeof(uid2), cudaMemcpyDeviceToHost, g->stream));
+  LUXB_CUDA(cudaStreamSynchronize(g->stream));
+  LUXB_CUDA(cudaFree(d_id));
+  LUXB_NCCL(nccl().CommInitRank(&g->comm2, g->P, uid2, g->cfg.rank));
+  LUXB_CUDA(cudaStreamCreateWithFlags(&g->stream2, cudaStreamNonBlocking));
+  LUXB_CUDA(cudaEventCreateWithFlags(&g->ev_pack, cudaEventDisableTiming));
+  LUXB_CUDA(cudaEventCreateWithFlags(&g->ev_cold, cudaEventDisableTiming));
   return 0;
 }
 
@@ -928,6 +944,7 @@ static int build_hot_layout(luxb_graph* g, bool compact_cold) {
 static int allgather_slices(luxb_graph* g, void* replica, size_t elem_bytes);
 static int build_seg_sweep(luxb_graph* g);
 static int pagerank_publish(luxb_graph* g, float* x_new);
+static int wait_cold_exchange(luxb_graph* g);
 
 int luxb_init(luxb_graph* g) {
   LUXB_ARG(g != nullptr, "graph is NULL");
@@ -955,10 +972,12 @@ int luxb_init(luxb_graph* g) {
         LUXB_TRY(set_l2_persisting_window(g, g->d_hot, (size_t)g->hot_n * 4));
       }
       if (g->packed) {
-        g->xt_chunk = ((((uint64_t)g->hot_n + g->cold_n + g->P - 1) / g->P) + 31) & ~31ull;
+        g->xt_hot_chunk = ((((uint64_t)g->hot_n + g->P - 1) / g->P) + 31) & ~31ull;
+        g->xt_cold_chunk = ((((uint64_t)g->cold_n + g->P - 1) / g->P) + 31) & ~31ull;
+        const uint64_t xt_len = (g->xt_hot_chunk + g->xt_cold_chunk) * g->P;
         for (int k = 0; k < 2; ++k) {
-          LUXB_TRY(dmalloc(&g->d_xt[k], g->xt_chunk * g->P));
-          LUXB_CUDA(cudaMemsetAsync(g->d_xt[k], 0, g->xt_chunk * g->P * 4, g->stream));
+          LUXB_TRY(dmalloc(&g->d_xt[k], xt_len));
+          LUXB_CUDA(cudaMemsetAsync(g->d_xt[k], 0, xt_len * 4, g->stream));
         }
       }
       LUXB_CUDA(cudaGetLastError());
@@ -1552,6 +1571,7 @@ static int launch_seg_main(luxb_graph* g, const PullLayout& L, const typename Pr
   a.p.prm = prm;
   a.p.hub_bits = hub_bits;
   a.p.l2_hints = g->l2_hints;
+  LUXB_TRY(wait_cold_exchange(g));
   a.tile_counter = reinterpret_cast<uint32_t*>(g->d_counters + 2);
   LUXB_CUDA(cudaMemsetAsync(a.tile_counter, 0, 4, g->stream));
   switch (g->seg_main_shape) {
@@ -1651,46 +1671,67 @@ static int pagerank_publish(luxb_graph* g, float* x_new) {
     }
     return 0;
   }
+  LUXB_TRY(wait_cold_exchange(g));  // back-to-back publishes (set_values after init): the buffer about to be packed is quiescent
   float* XTn = g->d_xt[1 - g->cur_xt];
   const uint32_t H = g->hot_n;
+  const uint64_t Ch = g->xt_hot_chunk, Cc = g->xt_cold_chunk, cold_base = Ch * g->P;  // XT = [P hot chunks | P cold chunks]
   const uint32_t nh_me = g->hot_off[me + 1] - g->hot_off[me], nc_me = g->cold_off[me + 1] - g->cold_off[me];
   if (nh_me + nc_me) {
     pack_values_kernel<float><<<grid_for((uint64_t)nh_me + nc_me, 256, grid), 256, 0, g->stream>>>(
-        x_new + g->row_left, g->d_pack_list, nh_me, nc_me, XTn + g->hot_off[me], XTn + H + g->cold_off[me]);
+        x_new + g->row_left, g->d_pack_list, nh_me, nc_me, XTn + g->hot_off[me], XTn + cold_base + g->cold_off[me]);
     LUXB_CUDA(cudaGetLastError());
     g->stats.kernel_launches++;
   }
-  if (g->p2p_ready && g->cfg.exchange != LUXB_EXCHANGE_NCCL) {
-    const uint64_t C = g->xt_chunk;
-    const uint64_t rng[2][2] = {{g->hot_off[me], g->hot_off[me + 1]}, {(uint64_t)H + g->cold_off[me], (uint64_t)H + g->cold_off[me + 1]}};
-    for (int r = 0; r < 2; ++r)
+  LUXB_CUDA(cudaEventRecord(g->ev_pack, g->stream));
+  const bool p2p = g->p2p_ready && g->cfg.exchange != LUXB_EXCHANGE_NCCL;
+  // one balanced all-gather of a region of XT: re-chunk copies into the peers' XT, barrier, ncclAllGather of equal chunks
+  auto exchange_region = [&](uint64_t base, uint64_t C, uint64_t lo_own, uint64_t hi_own, const uint32_t* off, cudaStream_t st,
+                             ncclComm_t comm, uint32_t** d_sync) -> int {
+    if (p2p) {
       for (int k = 0; k < g->P; ++k) {
         if (k == me) continue;
-        const uint64_t lo = std::max<uint64_t>(rng[r][0], k * C), hi = std::min<uint64_t>(rng[r][1], (k + 1) * C);
+        const uint64_t lo = std::max<uint64_t>(lo_own, k * C), hi = std::min<uint64_t>(hi_own, (k + 1) * C);
         if (lo < hi)
-          LUXB_CUDA(cudaMemcpyAsync(reinterpret_cast<float*>(g->peer_xt[1 - g->cur_xt][k]) + lo, XTn + lo, (hi - lo) * 4, cudaMemcpyDefault,
-                                    g->stream));
+          LUXB_CUDA(cudaMemcpyAsync(reinterpret_cast<float*>(g->peer_xt[1 - g->cur_xt][k]) + base + lo, XTn + base + lo, (hi - lo) * 4,
+                                    cudaMemcpyDefault, st));
       }
-    pt_mark(g, 3);
-    LUXB_TRY(p2p_barrier(g));
-    LUXB_NCCL(nccl().AllGather(XTn + me * C, XTn, C, ncclFloat32, g->comm, g->stream));
-    pt_mark(g, 4);
-  } else {
-    LUXB_NCCL(nccl().GroupStart());
-    for (int p = 0; p < g->P; ++p) {
-      const uint32_t nh = g->hot_off[p + 1] - g->hot_off[p], nc = g->cold_off[p + 1] - g->cold_off[p];
-      if (nh) LUXB_NCCL(nccl().Broadcast(XTn + g->hot_off[p], XTn + g->hot_off[p], nh, ncclFloat32, p, g->comm, g->stream));
-      if (nc) LUXB_NCCL(nccl().Broadcast(XTn + H + g->cold_off[p], XTn + H + g->cold_off[p], nc, ncclFloat32, p, g->comm, g->stream));
+      if (!*d_sync) LUXB_TRY(dmalloc(d_sync, 4));
+      LUXB_NCCL(nccl().AllReduce(*d_sync, *d_sync, 1, ncclUint32, ncclSum, comm, st));  // every re-chunk copy has landed
+      LUXB_NCCL(nccl().AllGather(XTn + base + me * C, XTn + base, C, ncclFloat32, comm, st));
+    } else {
+      LUXB_NCCL(nccl().GroupStart());
+      for (int p = 0; p < g->P; ++p) {
+        const uint32_t n = off[p + 1] - off[p];
+        if (n) LUXB_NCCL(nccl().Broadcast(XTn + base + off[p], XTn + base + off[p], n, ncclFloat32, p, comm, st));
+      }
+      LUXB_NCCL(nccl().GroupEnd());
     }
-    LUXB_NCCL(nccl().GroupEnd());
-    pt_mark(g, 3);
-  }
+    return 0;
+  };
+  // hot part on the compute stream: the next sweep's panel gather needs it first
+  LUXB_TRY(exchange_region(0, Ch, g->hot_off[me], g->hot_off[me + 1], g->hot_off, g->stream, g->comm, &g->d_sync));
+  pt_mark(g, 3);
   hot_permute_kernel<float><<<grid_for(H, 256, grid), 256, 0, g->stream>>>((float*)g->d_hot, XTn, g->d_zperm, H);
   LUXB_CUDA(cudaGetLastError());
   g->stats.kernel_launches++;
   pt_mark(g, 2);
+  // cold part on the second stream / communicator: only the next MAIN sweep reads it, so it overlaps with the next
+  // sweep's panel kernel (launch_seg_main waits for ev_cold)
+  LUXB_CUDA(cudaStreamWaitEvent(g->stream2, g->ev_pack, 0));
+  LUXB_TRY(exchange_region(cold_base, Cc, g->cold_off[me], g->cold_off[me + 1], g->cold_off, g->stream2, g->comm2, &g->d_sync2));
+  LUXB_CUDA(cudaEventRecord(g->ev_cold, g->stream2));
+  g->cold_pending = true;
   g->cur_xt ^= 1;
   g->replica_stale = true;
+  return 0;
+}
+
+// the cold values of the previous exchange must have arrived before anything gathers them
+static int wait_cold_exchange(luxb_graph* g) {
+  if (g->cold_pending) {
+    LUXB_CUDA(cudaStreamWaitEvent(g->stream, g->ev_cold, 0));
+    g->cold_pending = false;
+  }
   return 0;
 }
 
@@ -1701,10 +1742,11 @@ static int pagerank_iteration(luxb_graph* g) {
   prm.deg = g->d_deg;
   float* x_old = (float*)g->d_val[g->cur];
   float* x_new = (float*)g->d_val[1 - g->cur];
-  const float* x_cold = g->packed ? g->d_xt[g->cur_xt] + g->hot_n : x_old;
+  const float* x_cold = g->packed ? g->d_xt[g->cur_xt] + g->xt_hot_chunk * g->P : x_old;
   if (g->seg_on) {
     LUXB_TRY((sweep_seg<PageRankProgram>(g, x_old, x_cold, x_new + g->row_left, 1 - g->cur, prm)));
   } else {
+    LUXB_TRY(wait_cold_exchange(g));
     LUXB_TRY(launch_pull<PageRankProgram>(g, base_layout(g, g->hot_n ? g->d_src_gather : g->d_src), x_old, x_cold, (const float*)g->d_hot,
                                           g->hot_n, x_new + g->row_left, prm));
   }
@@ -1820,123 +1862,140 @@ static int label_iteration(luxb_graph* g) {
     }
   }
 
-  // ---- new frontier of this partition (components_gpu.cu:462-491) ----
   const int fgrid = grid_for(g->n_part, 256, g->num_sms * 8);
   uint32_t count = 0;
-  if (dense_fq) {
-    if (g->n_part) {
-      frontier_diff_kernel<<<fgrid, 256, 0, g->stream>>>(lab + g->row_left, g->d_cur, g->n_part, new_slot);
-      g->stats.kernel_launches++;
+  uint64_t total = 0;
+  FrontierHeader my_hdr{LUXB_SPARSE_QUEUE, 0};
+  const bool dev_frontier = g->P == 1 || (g->p2p_ready && g->cfg.exchange != LUXB_EXCHANGE_NCCL);
+  if (dev_frontier) {
+    // ---- new frontier + exchange WITHOUT host round trips: the representation rules (components_gpu.cu:462-491) run on
+    // the device (push.cuh), the published slot and labels are stored straight into every rank's slot table / label
+    // replica (frontier P2P push), and the host reads the P headers once, at the end of the iteration ----
+    unsigned char* slot_d = dense_fq ? new_slot : g->d_fq_tmp;   // bitmap candidate
+    unsigned char* slot_s = dense_fq ? g->d_fq_tmp : new_slot;   // queue candidate (filled by the push kernels)
+    LUXB_CUDA(cudaMemsetAsync(dense_fq ? slot_s : slot_d, 0, 8, g->stream));
+    if (!g->d_fctl) LUXB_TRY(dmalloc(&g->d_fctl, 1));
+    if (dense_fq) frontier_diff_kernel<<<fgrid, 256, 0, g->stream>>>(lab + g->row_left, g->d_cur, g->n_part, slot_d);
+    frontier_fix_kernel<<<1, 32, 0, g->stream>>>(slot_d, slot_s, max_nodes, dense_fq ? 1 : 0, g->d_fctl);
+    frontier_d2s_if_kernel<<<fgrid, 256, 0, g->stream>>>(&g->d_fctl->need_d2s, slot_d, g->row_left, g->n_part, slot_s, max_nodes);
+    frontier_diff_if_kernel<<<fgrid, 256, 0, g->stream>>>(&g->d_fctl->need_promote, lab + g->row_left, g->d_cur, g->n_part, slot_d);
+    frontier_final_kernel<<<1, 32, 0, g->stream>>>(slot_d, slot_s, dense_fq ? 1 : 0, g->d_fctl);
+    frontier_pack_labels_if_kernel<<<grid_for(max_nodes, 256, g->num_sms * 4), 256, 0, g->stream>>>(&g->d_fctl->final_sparse, slot_s, max_nodes,
+                                                                                                  g->row_left, g->d_cur);
+    LUXB_CUDA(cudaGetLastError());
+    g->stats.kernel_launches += dense_fq ? 6 : 5;
+    // barrier: every rank has finished the kernels that read this iteration's slots and labels
+    if (g->P > 1) LUXB_TRY(p2p_barrier(g));
+    FrontierPushArgs fa{};
+    fa.ctl = g->d_fctl;
+    fa.slot_d = slot_d;
+    fa.slot_s = slot_s;
+    fa.cur = g->d_cur;
+    fa.n_part = g->n_part;
+    fa.cap = g->cap[me];
+    fa.row_left = g->row_left;
+    fa.n_dst = 0;
+    for (int p = 0; p < g->P; ++p) {
+      unsigned char* fq_p = (p == me) ? g->d_fq_all : reinterpret_cast<unsigned char*>(g->peer_fq[p]);
+      uint32_t* lab_p = (p == me) ? lab : reinterpret_cast<uint32_t*>(g->peer_val[0][p]);
+      fa.dst_slot[fa.n_dst] = fq_p + g->slot_off[me];
+      fa.dst_lab[fa.n_dst] = lab_p;
+      fa.n_dst++;
     }
-    LUXB_CUDA(cudaMemcpyAsync(g->h_scratch, new_slot, 8, cudaMemcpyDeviceToHost, g->stream));
-    LUXB_CUDA(cudaStreamSynchronize(g->stream));
-    count = g->h_scratch[1];
-    if (count < max_nodes) {  // demote to a queue
-      LUXB_CUDA(cudaMemsetAsync(g->d_fq_tmp, 0, 8, g->stream));
-      if (count) {
-        frontier_d2s_kernel<<<fgrid, 256, 0, g->stream>>>(new_slot, g->row_left, g->n_part, g->d_fq_tmp, max_nodes);
+    frontier_push_kernel<<<g->num_sms * 2, 512, 0, g->stream>>>(fa);
+    LUXB_CUDA(cudaGetLastError());
+    g->stats.kernel_launches++;
+    if (g->P > 1) LUXB_TRY(p2p_barrier(g));  // all pushes have landed
+    PartTable pt{};
+    pt.P = g->P;
+    if (!g->d_slot_off) {
+      LUXB_TRY(dmalloc(&g->d_slot_off, LUXB_MAX_PARTS));
+      LUXB_CUDA(cudaMemcpyAsync(g->d_slot_off, g->slot_off, sizeof(uint64_t) * g->P, cudaMemcpyHostToDevice, g->stream));
+    }
+    frontier_headers_kernel<<<1, LUXB_MAX_PARTS, 0, g->stream>>>(g->d_fq_all, pt, g->d_slot_off, g->d_hdr_all);
+    LUXB_CUDA(cudaMemcpyAsync(g->h_hdr, g->d_hdr_all, (size_t)g->P * 8, cudaMemcpyDeviceToHost, g->stream));
+    LUXB_CUDA(cudaStreamSynchronize(g->stream));  // the iteration's one host synchronisation
+    my_hdr.type = g->h_hdr[2 * me];
+    my_hdr.num_nodes = count = g->h_hdr[2 * me + 1];
+    for (int p = 0; p < g->P; ++p) total += g->h_hdr[2 * p + 1];
+  } else {
+    // ---- new frontier of this partition (components_gpu.cu:462-491) ----
+    if (dense_fq) {
+      if (g->n_part) {
+        frontier_diff_kernel<<<fgrid, 256, 0, g->stream>>>(lab + g->row_left, g->d_cur, g->n_part, new_slot);
         g->stats.kernel_launches++;
       }
-      std::swap(g->d_fq_new, g->d_fq_tmp);
-      new_slot = g->d_fq_new;
-      dense_fq = false;
-    }
-  } else {
-    LUXB_CUDA(cudaMemcpyAsync(g->h_scratch, new_slot, 8, cudaMemcpyDeviceToHost, g->stream));
-    LUXB_CUDA(cudaStreamSynchronize(g->stream));
-    count = g->h_scratch[1];
-    if (count >= max_nodes) {  // promote: rebuild as a bitmap from the label diff (count is re-derived exactly)
-      dense_fq = true;
-      LUXB_CUDA(cudaMemsetAsync(new_slot, 0, 8, g->stream));
-      frontier_diff_kernel<<<fgrid, 256, 0, g->stream>>>(lab + g->row_left, g->d_cur, g->n_part, new_slot);
-      g->stats.kernel_launches++;
       LUXB_CUDA(cudaMemcpyAsync(g->h_scratch, new_slot, 8, cudaMemcpyDeviceToHost, g->stream));
       LUXB_CUDA(cudaStreamSynchronize(g->stream));
       count = g->h_scratch[1];
-    }
-  }
-  FrontierHeader my_hdr{dense_fq ? LUXB_DENSE_BITMAP : LUXB_SPARSE_QUEUE, count};
-  LUXB_CUDA(cudaMemcpyAsync(new_slot, &my_hdr, 8, cudaMemcpyHostToDevice, g->stream));
-  if (!dense_fq && count) {
-    frontier_pack_labels_kernel<<<grid_for(count, 256, g->num_sms * 4), 256, 0, g->stream>>>(new_slot, max_nodes, g->row_left,
-                                                                                            g->d_cur);
-    g->stats.kernel_launches++;
-  }
-  LUXB_CUDA(cudaGetLastError());
-
-  // ---- exchange: headers, then payload sized by each partition's representation ----
-  if (g->P > 1) {
-    LUXB_NCCL(nccl().AllGather(new_slot, g->d_hdr_all, 8, ncclUint8, g->comm, g->stream));
-    LUXB_CUDA(cudaMemcpyAsync(g->h_hdr, g->d_hdr_all, (size_t)g->P * 8, cudaMemcpyDeviceToHost, g->stream));
-    LUXB_CUDA(cudaStreamSynchronize(g->stream));
-  } else {
-    g->h_hdr[0] = my_hdr.type;
-    g->h_hdr[1] = my_hdr.num_nodes;
-  }
-  uint64_t total = 0;
-  for (int p = 0; p < g->P; ++p) total += g->h_hdr[2 * p + 1];
-  if (g->P > 1 && g->p2p_ready && g->cfg.exchange != LUXB_EXCHANGE_NCCL) {
-    // Frontier P2P push: this partition's new frontier slot — header + bitmap, or header + (id, label) pairs —
-    // and, for a dense frontier, its label slice are stored straight into EVERY peer's slot table / label replica over
-    // NVLink by one kernel (128-bit stores; disjoint ranges, no atomics across GPUs).  Barrier before: every rank has
-    // finished the kernels that read this iteration's slots and labels; barrier after: all pushes have landed.
-    LUXB_TRY(p2p_barrier(g));
-    PushRegions r{};
-    const uint32_t my_type = g->h_hdr[2 * me], my_cnt = g->h_hdr[2 * me + 1];
-    const size_t slot_off = g->slot_off[me];
-    r.n_peers = 0;
-    for (int p = 0; p < g->P; ++p) {
-      unsigned char* fq_p = reinterpret_cast<unsigned char*>(g->peer_fq[p]);
-      uint32_t* lab_p = reinterpret_cast<uint32_t*>(g->peer_val[0][p]);
-      r.dst[0][r.n_peers] = reinterpret_cast<uint32_t*>(fq_p + slot_off);
-      if (my_type == LUXB_DENSE_BITMAP) r.dst[1][r.n_peers] = lab_p + g->rl[me];
-      else r.dst[1][r.n_peers] = reinterpret_cast<uint32_t*>(fq_p + slot_off + 8 + (size_t)g->cap[me] * 4);
-      r.n_peers++;
-    }
-    r.src[0] = reinterpret_cast<const uint32_t*>(new_slot);
-    r.n_regions = 1;
-    if (my_cnt && g->n_part) {
-      if (my_type == LUXB_DENSE_BITMAP) {
-        r.words[0] = 2 + ((size_t)g->n_part + 31) / 32;
-        r.src[1] = g->d_cur;
-        r.words[1] = g->n_part;
-      } else {
-        r.words[0] = 2 + my_cnt;
-        r.src[1] = reinterpret_cast<const uint32_t*>(new_slot + 8 + (size_t)g->cap[me] * 4);
-        r.words[1] = my_cnt;
+      if (count < max_nodes) {  // demote to a queue
+        LUXB_CUDA(cudaMemsetAsync(g->d_fq_tmp, 0, 8, g->stream));
+        if (count) {
+          frontier_d2s_kernel<<<fgrid, 256, 0, g->stream>>>(new_slot, g->row_left, g->n_part, g->d_fq_tmp, max_nodes);
+          g->stats.kernel_launches++;
+        }
+        std::swap(g->d_fq_new, g->d_fq_tmp);
+        new_slot = g->d_fq_new;
+        dense_fq = false;
       }
-      r.n_regions = 2;
     } else {
-      r.words[0] = 2;
-    }
-    p2p_push_kernel<<<g->num_sms * 2, 512, 0, g->stream>>>(r);
-    LUXB_CUDA(cudaGetLastError());
-    g->stats.kernel_launches++;
-    LUXB_TRY(p2p_barrier(g));
-  } else if (g->P > 1) {
-    LUXB_NCCL(nccl().GroupStart());
-    for (int p = 0; p < g->P; ++p) {
-      uint32_t type = g->h_hdr[2 * p], cnt = g->h_hdr[2 * p + 1];
-      unsigned char* dst_slot = slot_ptr(g->d_fq_all, g, p);
-      const unsigned char* send_slot = p == me ? new_slot : dst_slot;
-      LUXB_NCCL(nccl().Broadcast(send_slot, dst_slot, 8, ncclUint8, p, g->comm, g->stream));
-      if (cnt == 0 || g->np[p] == 0) continue;
-      if (type == LUXB_DENSE_BITMAP) {
-        size_t bm_bytes = (((size_t)g->np[p] + 31) / 32) * 4;
-        LUXB_NCCL(nccl().Broadcast(send_slot + 8, dst_slot + 8, bm_bytes, ncclUint8, p, g->comm, g->stream));
-        const void* send_lab = p == me ? (const void*)g->d_cur : (const void*)(lab + g->rl[p]);
-        LUXB_NCCL(nccl().Broadcast(send_lab, lab + g->rl[p], (size_t)g->np[p] * 4, ncclUint8, p, g->comm, g->stream));
-      } else {
-        size_t qoff = 8 + (size_t)g->cap[p] * 4;
-        LUXB_NCCL(nccl().Broadcast(send_slot + 8, dst_slot + 8, (size_t)cnt * 4, ncclUint8, p, g->comm, g->stream));
-        LUXB_NCCL(nccl().Broadcast(send_slot + qoff, dst_slot + qoff, (size_t)cnt * 4, ncclUint8, p, g->comm, g->stream));
+      LUXB_CUDA(cudaMemcpyAsync(g->h_scratch, new_slot, 8, cudaMemcpyDeviceToHost, g->stream));
+      LUXB_CUDA(cudaStreamSynchronize(g->stream));
+      count = g->h_scratch[1];
+      if (count >= max_nodes) {  // promote: rebuild as a bitmap from the label diff (count is re-derived exactly)
+        dense_fq = true;
+        LUXB_CUDA(cudaMemsetAsync(new_slot, 0, 8, g->stream));
+        frontier_diff_kernel<<<fgrid, 256, 0, g->stream>>>(lab + g->row_left, g->d_cur, g->n_part, new_slot);
+        g->stats.kernel_launches++;
+        LUXB_CUDA(cudaMemcpyAsync(g->h_scratch, new_slot, 8, cudaMemcpyDeviceToHost, g->stream));
+        LUXB_CUDA(cudaStreamSynchronize(g->stream));
+        count = g->h_scratch[1];
       }
     }
-    LUXB_NCCL(nccl().GroupEnd());
-  } else {
-    LUXB_CUDA(cudaMemcpyAsync(g->d_fq_all, new_slot, g->slot_bytes[0], cudaMemcpyDeviceToDevice, g->stream));
-    if (dense_fq && count && g->n_part)
-      LUXB_CUDA(cudaMemcpyAsync(lab + g->row_left, g->d_cur, (size_t)g->n_part * 4, cudaMemcpyDeviceToDevice, g->stream));
+    my_hdr = FrontierHeader{dense_fq ? LUXB_DENSE_BITMAP : LUXB_SPARSE_QUEUE, count};
+    LUXB_CUDA(cudaMemcpyAsync(new_slot, &my_hdr, 8, cudaMemcpyHostToDevice, g->stream));
+    if (!dense_fq && count) {
+      frontier_pack_labels_kernel<<<grid_for(count, 256, g->num_sms * 4), 256, 0, g->stream>>>(new_slot, max_nodes, g->row_left,
+                                                                                              g->d_cur);
+      g->stats.kernel_launches++;
+    }
+    LUXB_CUDA(cudaGetLastError());
+
+    // ---- exchange: headers, then payload sized by each partition's representation ----
+    if (g->P > 1) {
+      LUXB_NCCL(nccl().AllGather(new_slot, g->d_hdr_all, 8, ncclUint8, g->comm, g->stream));
+      LUXB_CUDA(cudaMemcpyAsync(g->h_hdr, g->d_hdr_all, (size_t)g->P * 8, cudaMemcpyDeviceToHost, g->stream));
+      LUXB_CUDA(cudaStreamSynchronize(g->stream));
+    } else {
+      g->h_hdr[0] = my_hdr.type;
+      g->h_hdr[1] = my_hdr.num_nodes;
+    }
+    for (int p = 0; p < g->P; ++p) total += g->h_hdr[2 * p + 1];
+    if (g->P > 1) {
+      LUXB_NCCL(nccl().GroupStart());
+      for (int p = 0; p < g->P; ++p) {
+        uint32_t type = g->h_hdr[2 * p], cnt = g->h_hdr[2 * p + 1];
+        unsigned char* dst_slot = slot_ptr(g->d_fq_all, g, p);
+        const unsigned char* send_slot = p == me ? new_slot : dst_slot;
+        LUXB_NCCL(nccl().Broadcast(send_slot, dst_slot, 8, ncclUint8, p, g->comm, g->stream));
+        if (cnt == 0 || g->np[p] == 0) continue;
+        if (type == LUXB_DENSE_BITMAP) {
+          size_t bm_bytes = (((size_t)g->np[p] + 31) / 32) * 4;
+          LUXB_NCCL(nccl().Broadcast(send_slot + 8, dst_slot + 8, bm_bytes, ncclUint8, p, g->comm, g->stream));
+          const void* send_lab = p == me ? (const void*)g->d_cur : (const void*)(lab + g->rl[p]);
+          LUXB_NCCL(nccl().Broadcast(send_lab, lab + g->rl[p], (size_t)g->np[p] * 4, ncclUint8, p, g->comm, g->stream));
+        } else {
+          size_t qoff = 8 + (size_t)g->cap[p] * 4;
+          LUXB_NCCL(nccl().Broadcast(send_slot + 8, dst_slot + 8, (size_t)cnt * 4, ncclUint8, p, g->comm, g->stream));
+          LUXB_NCCL(nccl().Broadcast(send_slot + qoff, dst_slot + qoff, (size_t)cnt * 4, ncclUint8, p, g->comm, g->stream));
+        }
+      }
+      LUXB_NCCL(nccl().GroupEnd());
+    } else {
+      LUXB_CUDA(cudaMemcpyAsync(g->d_fq_all, new_slot, g->slot_bytes[0], cudaMemcpyDeviceToDevice, g->stream));
+      if (dense_fq && count && g->n_part)
+        LUXB_CUDA(cudaMemcpyAsync(lab + g->row_left, g->d_cur, (size_t)g->n_part * 4, cudaMemcpyDeviceToDevice, g->stream));
+    }
   }
   for (int p = 0; p < g->P; ++p) {
     uint32_t type = g->h_hdr[2 * p], cnt = g->h_hdr[2 * p + 1];
@@ -1968,6 +2027,7 @@ static int one_iteration(luxb_graph* g) {
 }
 
 static int finish_timed(luxb_graph* g) {
+  LUXB_TRY(wait_cold_exchange(g));  // the loop time includes the overlapped part of the last exchange
   pt_flush(g);
   LUXB_CUDA(cudaEventRecord(g->ev_end, g->stream));
   LUXB_CUDA(cudaStreamSynchronize(g->stream));
@@ -2231,7 +2291,13 @@ void luxb_close(luxb_graph* g) {
   if (g->stream) cudaStreamSynchronize(g->stream);
   if (g->d_hot) cudaCtxResetPersistingL2Cache();  // release the lines pinned for the hot copies
   p2p_unmap(g);
+  if (g->stream2) cudaStreamSynchronize(g->stream2);
+  if (g->comm2) nccl().CommDestroy(g->comm2);
   if (g->comm) nccl().CommDestroy(g->comm);
+  if (g->ev_pack) cudaEventDestroy(g->ev_pack);
+  if (g->ev_cold) cudaEventDestroy(g->ev_cold);
+  if (g->stream2) cudaStreamDestroy(g->stream2);
+  if (g->d_sync2) cudaFree(g->d_sync2);
   void* ptrs[] = {g->d_row_end, g->d_row_end32, g->d_src, g->d_weight, g->d_tile_v, g->d_head, g->d_tail, g->d_deg, g->d_val[0], g->d_val[1],
                   g->d_cur, g->d_out_end, g->d_out_dst, g->d_fq_all, g->d_fq_new, g->d_fq_tmp, g->d_hdr_all, g->d_counters,
                   g->d_chunk_first, g->d_chunk_vtx, g->d_partial, g->d_sync, g->d_hot_order, g->d_src_gather,
@@ -2246,7 +2312,8 @@ void luxb_close(luxb_graph* g) {
   if (g->d_hub_vtx) cudaFree(g->d_hub_vtx);
   if (g->d_hub_bits) cudaFree(g->d_hub_bits);
   if (g->d_sb_partial) cudaFree(g->d_sb_partial);
-  for (void* q : {(void*)g->d_zperm, (void*)g->d_pack_list, (void*)g->d_xt[0], (void*)g->d_xt[1]}) if (q) cudaFree(q);
+  for (void* q : {(void*)g->d_zperm, (void*)g->d_pack_list, (void*)g->d_xt[0], (void*)g->d_xt[1], (void*)g->d_fctl, (void*)g->d_slot_off})
+    if (q) cudaFree(q);
   if (g->h_hdr) cudaFreeHost(g->h_hdr);
   if (g->h_scratch) cudaFreeHost(g->h_scratch);
   for (cudaEvent_t e : g->kt_events) cudaEventDestroy(e);

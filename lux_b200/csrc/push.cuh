@@ -9,6 +9,7 @@
 // Our slot additionally carries, after the queue ids, the queue's new labels (same capacity) so that a sparse
 // iteration exchanges (id, label) pairs instead of whole label slices.
 #pragma once
+#include "build.cuh"
 #include "common.cuh"
 #include "programs.cuh"
 
@@ -264,6 +265,140 @@ __global__ void frontier_apply_kernel(const unsigned char* __restrict__ slot, ui
   const uint32_t* queue = reinterpret_cast<const uint32_t*>(slot + sizeof(FrontierHeader));
   const uint32_t* qlab = queue + max_nodes;
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) lab[queue[k]] = qlab[k];
+}
+
+// ---- device-side frontier finalisation (components_gpu.cu:462-491 without host round trips) ------------------------
+// The partition's new frontier exists as a bitmap candidate (slot D: built by frontier_diff_kernel) and / or a queue
+// candidate (slot S: appended by the push kernels).  frontier_fix_kernel applies the reference's representation rules
+// on the device — bitmap with fewer than max_nodes vertices -> demote to a queue (:469), queue that overflowed ->
+// promote to a bitmap (:485) — the two conditional kernels run under device flags, frontier_final_kernel publishes the
+// header, frontier_push_kernel ships slot + labels to every rank.  The host reads the P headers once per iteration.
+struct FrontierCtl {
+  uint32_t need_d2s;      // demote: rebuild the queue from the bitmap
+  uint32_t need_promote;  // promote: rebuild the bitmap from the label diff
+  uint32_t final_sparse;  // representation that is published
+  uint32_t final_count;
+};
+
+__global__ void frontier_fix_kernel(unsigned char* slot_d, unsigned char* slot_s, uint32_t max_nodes, int dense_built, FrontierCtl* ctl) {
+  if (blockIdx.x || threadIdx.x) return;
+  FrontierHeader* hd = reinterpret_cast<FrontierHeader*>(slot_d);
+  FrontierHeader* hs = reinterpret_cast<FrontierHeader*>(slot_s);
+  ctl->need_d2s = 0;
+  ctl->need_promote = 0;
+  if (dense_built) {
+    if (hd->num_nodes < max_nodes) { ctl->need_d2s = 1; hs->num_nodes = 0; }  // the queue is rebuilt from the bitmap
+  } else if (hs->num_nodes >= max_nodes) {
+    ctl->need_promote = 1;
+    hd->num_nodes = 0;  // re-counted exactly by the diff (the reference over-counts here: defect B5)
+  }
+}
+
+__global__ void frontier_final_kernel(unsigned char* slot_d, unsigned char* slot_s, int dense_built, FrontierCtl* ctl) {
+  if (blockIdx.x || threadIdx.x) return;
+  FrontierHeader* hd = reinterpret_cast<FrontierHeader*>(slot_d);
+  FrontierHeader* hs = reinterpret_cast<FrontierHeader*>(slot_s);
+  const bool sparse = dense_built ? ctl->need_d2s != 0 : ctl->need_promote == 0;
+  ctl->final_sparse = sparse ? 1u : 0u;
+  if (sparse) { hs->type = LUXB_SPARSE_QUEUE; ctl->final_count = hs->num_nodes; }
+  else { hd->type = LUXB_DENSE_BITMAP; ctl->final_count = hd->num_nodes; }
+}
+
+// conditional variants: run only when *enable != 0 (the flags of FrontierCtl)
+__global__ void frontier_diff_if_kernel(const uint32_t* __restrict__ enable, const uint32_t* __restrict__ lab_slice,
+                                        const uint32_t* __restrict__ cur, uint32_t n_part, unsigned char* __restrict__ slot) {
+  if (enable && *enable == 0) return;
+  __shared__ uint32_t s_cnt;
+  FrontierHeader* hdr = reinterpret_cast<FrontierHeader*>(slot);
+  uint32_t* words = reinterpret_cast<uint32_t*>(slot + sizeof(FrontierHeader));
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  uint32_t local = 0;
+  uint32_t n_round = (n_part + 31) & ~31u;
+  for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_round; v += (uint64_t)gridDim.x * blockDim.x) {
+    bool ch = v < n_part && lab_slice[v] != cur[v];
+    unsigned m = __ballot_sync(0xffffffffu, ch);
+    if ((threadIdx.x & 31) == 0) { words[v >> 5] = m; local += __popc(m); }
+  }
+  if (local) atomicAdd(&s_cnt, local);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_cnt) atomicAdd(&hdr->num_nodes, s_cnt);
+}
+
+__global__ void frontier_d2s_if_kernel(const uint32_t* __restrict__ enable, const unsigned char* __restrict__ dense_slot, uint32_t row_left,
+                                       uint32_t n_part, unsigned char* __restrict__ sparse_slot, uint32_t max_nodes) {
+  if (*enable == 0) return;
+  const uint32_t* words = reinterpret_cast<const uint32_t*>(dense_slot + sizeof(FrontierHeader));
+  FrontierHeader* hdr = reinterpret_cast<FrontierHeader*>(sparse_slot);
+  uint32_t* queue = reinterpret_cast<uint32_t*>(sparse_slot + sizeof(FrontierHeader));
+  const unsigned lane = threadIdx.x & 31;
+  uint32_t n_round = (n_part + 31) & ~31u;
+  for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_round; v += (uint64_t)gridDim.x * blockDim.x) {
+    unsigned m = words[v >> 5];
+    if (m) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&hdr->num_nodes, (uint32_t)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if ((m >> lane) & 1) {
+        uint32_t pos = base + __popc(m & ((1u << lane) - 1));
+        if (pos < max_nodes) queue[pos] = row_left + (uint32_t)v;
+      }
+    }
+  }
+}
+
+__global__ void frontier_pack_labels_if_kernel(const uint32_t* __restrict__ enable, unsigned char* __restrict__ slot, uint32_t max_nodes,
+                                               uint32_t row_left, const uint32_t* __restrict__ cur) {
+  if (*enable == 0) return;
+  const FrontierHeader* hdr = reinterpret_cast<const FrontierHeader*>(slot);
+  const uint32_t* queue = reinterpret_cast<const uint32_t*>(slot + sizeof(FrontierHeader));
+  uint32_t* qlab = reinterpret_cast<uint32_t*>(slot + sizeof(FrontierHeader)) + max_nodes;
+  uint32_t n = hdr->num_nodes < max_nodes ? hdr->num_nodes : max_nodes;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) qlab[k] = cur[queue[k] - row_left];
+}
+
+// Frontier P2P push: this partition's published slot — header + bitmap, or header + (id, label) pairs — and,
+// for a bitmap, its label slice are stored straight into EVERY rank's slot table / label replica (peer pointers from
+// cudaIpcOpenMemHandle; NVLink stores; disjoint ranges, no atomics across GPUs).  Sizes come from the device header.
+struct FrontierPushArgs {
+  const FrontierCtl* ctl;
+  const unsigned char* slot_d;
+  const unsigned char* slot_s;
+  const uint32_t* cur;        // [n_part] this partition's labels
+  uint32_t n_part, cap, row_left;
+  int n_dst;
+  unsigned char* dst_slot[LUXB_MAX_PARTS];  // this partition's slot inside every rank's slot table (own rank included)
+  uint32_t* dst_lab[LUXB_MAX_PARTS];        // every rank's label replica
+};
+__global__ void frontier_push_kernel(const __grid_constant__ FrontierPushArgs a) {
+  const bool sparse = a.ctl->final_sparse != 0;
+  const uint32_t count = a.ctl->final_count;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(sparse ? a.slot_s : a.slot_d);
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (uint64_t)gridDim.x * blockDim.x;
+  const uint32_t q = sparse ? (count < a.cap ? count : a.cap) : 0;
+  const uint64_t words0 = 2 + (sparse ? (uint64_t)q : (count ? ((uint64_t)a.n_part + 31) / 32 : 0));
+  for (int p = 0; p < a.n_dst; ++p) {
+    uint32_t* d = reinterpret_cast<uint32_t*>(a.dst_slot[p]);
+    for (uint64_t i = tid; i < words0; i += nth) d[i] = src[i];  // header + bitmap words / queue ids
+    if (sparse) {
+      const uint32_t* ql = src + 2 + a.cap;
+      uint32_t* dl = d + 2 + a.cap;
+      for (uint64_t i = tid; i < q; i += nth) dl[i] = ql[i];     // the queue entries' labels
+    } else if (count) {
+      uint32_t* dl = a.dst_lab[p] + a.row_left;
+      for (uint64_t i = tid; i < a.n_part; i += nth) dl[i] = a.cur[i];  // label slice of a dense frontier
+    }
+  }
+}
+
+__global__ void frontier_headers_kernel(const unsigned char* __restrict__ fq_all, const __grid_constant__ PartTable pt,
+                                        const uint64_t* __restrict__ slot_off, uint32_t* __restrict__ hdr_out) {
+  const int p = threadIdx.x;
+  if (p < pt.P) {
+    const FrontierHeader* h = reinterpret_cast<const FrontierHeader*>(fq_all + slot_off[p]);
+    hdr_out[2 * p] = h->type;
+    hdr_out[2 * p + 1] = h->num_nodes;
+  }
 }
 
 // CheckTask invariants over this partition's in-edges (A.6).  CC: label[dst] >= label[src];

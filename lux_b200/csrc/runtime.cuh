@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "panel.cuh"
 #include "seg.cuh"
+#include "push.cuh"
 
 // one CSC swept by a merge-path tile kernel, with its tile table and fix-up scratch
 struct PullLayout {
@@ -101,7 +102,13 @@ struct luxb_graph {
   uint32_t* d_pack_list = nullptr;           // local indices of this rank's [hot | cold-active] vertices in transfer order
   float* d_xt[2] = {nullptr, nullptr};
   int cur_xt = 0;
-  uint64_t xt_chunk = 0;                     // equal chunk (elements) of the balanced all-gather over XT
+  uint64_t xt_hot_chunk = 0, xt_cold_chunk = 0;  // equal chunks (elements) of the two balanced all-gathers; XT = [P hot chunks | P cold chunks]
+  // the cold part of the exchange runs on a second stream / communicator, overlapped with the next sweep's panel gather
+  cudaStream_t stream2 = nullptr;
+  luxb::ncclComm_t comm2 = nullptr;
+  cudaEvent_t ev_pack = nullptr, ev_cold = nullptr;
+  bool cold_pending = false;                 // ev_cold has been recorded and not yet waited for by a main sweep
+  uint32_t* d_sync2 = nullptr;
   void* peer_xt[2][LUXB_MAX_PARTS]{};
   bool replica_stale = false;                // natural-order replica holds only this rank's slice (gathered on demand)
   // push apps
@@ -114,6 +121,8 @@ struct luxb_graph {
   unsigned char* d_fq_new = nullptr;  // this partition's slot under construction
   unsigned char* d_fq_tmp = nullptr;
   uint32_t* d_hdr_all = nullptr;      // [2 * P] gathered headers
+  luxb::FrontierCtl* d_fctl = nullptr;  // device-side frontier finalisation flags (push.cuh)
+  uint64_t* d_slot_off = nullptr;
   uint32_t* h_hdr = nullptr;          // pinned [2 * P]: type, count of the current frontier of every partition
   uint32_t* h_scratch = nullptr;      // pinned scratch (header readback)
   unsigned long long* d_counters = nullptr;  // [0] edges scanned by push kernels, [1] check mistakes
