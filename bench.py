@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--reference-split", action="store_true",
+                    help="N > 1: work on the reference's greedy edge-balanced split instead of the cost-balanced one")
     return ap.parse_args()
 
 
@@ -183,7 +185,9 @@ def main():
               "rmat": "a,b,c,d=.57,.19,.19,.05 edge_factor %d, duplicates and self-loops kept" % args.edge_factor,
               "l2_policy": "inputs larger than L2 (CSC slice %.1f GB + %.0f MB value replica per GPU vs 126 MB L2)" % (
                   (4 * ne + 8 * nv) / args.gpus / 1e9, 4 * nv / 1e6),
-              "parallelism": "dst-range partitions x%d (reference greedy edge-balanced split)" % args.gpus}
+              "parallelism": "dst-range partitions x%d (%s)" % (args.gpus, "reference greedy edge-balanced split" if (
+                  args.gpus == 1 or args.reference_split) else "contiguous ranges cut by estimated sweep cost — cfg.balanced_split; "
+                  "luxb_partition_bounds still reports the reference's greedy edge-balanced split")}
 
     if args.impl == "reference":
         if rank != 0:
@@ -239,7 +243,8 @@ def main():
         args.exchange = "p2p"
     exchange = {"p2p": L.EXCHANGE_P2P, "p2p_fused": L.EXCHANGE_P2P_FUSED, "nccl": L.EXCHANGE_NCCL}[args.exchange]
     t_build0 = time.perf_counter()
-    g = L.LuxGraph.from_rmat(scale, nv, ne, SEED, rank=rank, nranks=world, device=local, exchange=exchange)
+    g = L.LuxGraph.from_rmat(scale, nv, ne, SEED, rank=rank, nranks=world, device=local, exchange=exchange,
+                             balanced=not args.reference_split)
     g.comm_init_torch()
     g.init()
     if world > 1 and exchange != L.EXCHANGE_NCCL:
@@ -376,7 +381,7 @@ def main():
         if rank == 0:
             import oracle as O
             O.set_num_threads(os.cpu_count() or 1)  # torch.distributed.run exports OMP_NUM_THREADS=1 to every rank
-            b = g.bounds()
+            b = g.work_bounds()
             cover = [0, nv - 1]
             for p in range(world):
                 cover += [int(b["row_left"][p]), int(b["row_right"][p]) & 0xFFFFFFFF]

@@ -78,6 +78,10 @@ typedef struct {
   luxb_vid start_vtx;  /* SSSP -start (sssp.cc) */
   luxb_exchange exchange;
   int verbose;         /* -verbose: per-iteration line like components_gpu.cu:516-518 */
+  int balanced_split;  /* pull apps on several ranks: 1 = split the destination range by estimated sweep cost instead of
+                          by edge count (contiguous ranges, only the cut points move; results depend on the split only
+                          through float summation order).  luxb_partition_bounds keeps reporting the reference's split,
+                          luxb_work_bounds the one in use.  0 = the reference's split is the work split. */
   int zero_copy_edges; /* 1: keep the edge arrays (source ids, weights) in mapped pinned HOST memory and stream them
                           over PCIe every iteration — the analogue of Legion's -ll:zsize zero-copy memory for
                           graphs larger than HBM (lux_mapper.cc:146-165); vertex arrays stay in HBM */
@@ -114,6 +118,9 @@ int luxb_graph_info(const luxb_graph* g, luxb_vid* nv, luxb_eid* ne, int* nranks
 /* nranks entries each; fq_* are the frontier-slot byte ranges of push_model.inl:393-397 (NULL to skip). */
 int luxb_partition_bounds(const luxb_graph* g, luxb_vid* row_left, luxb_vid* row_right, luxb_eid* col_left,
                           uint64_t* fq_left, uint64_t* fq_right);
+/* The split of the destination range the ranks actually work on (== the reference's unless cfg.balanced_split);
+ * returns 1 when it is the cost-balanced one. */
+int luxb_work_bounds(const luxb_graph* g, luxb_vid* row_left, luxb_vid* row_right, luxb_eid* col_left);
 /* The reference partitioner on host arrays, without a handle (pull_model.inl:108-131).  Returns the number of
  * partitions the greedy scan produces (may differ from P; the reference asserts equality). */
 int luxb_partition_csc(luxb_vid nv, luxb_eid ne, const luxb_eid* row_end, int P, luxb_vid* row_left,

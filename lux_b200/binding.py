@@ -28,7 +28,8 @@ class _Csc(C.Structure):
 
 class _Config(C.Structure):
     _fields_ = [("app", C.c_int), ("rank", C.c_int), ("nranks", C.c_int), ("device", C.c_int),
-                ("start_vtx", C.c_uint32), ("exchange", C.c_int), ("verbose", C.c_int), ("zero_copy_edges", C.c_int)]
+                ("start_vtx", C.c_uint32), ("exchange", C.c_int), ("verbose", C.c_int), ("balanced_split", C.c_int),
+                ("zero_copy_edges", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -55,7 +56,7 @@ def declared_symbols():
     return sorted(set(re.findall(r"\b(luxb_[a-z0-9_]+)\s*\(", text)))
 
 
-ABI_VERSION = 2  # must equal luxb_abi_version(): layout of luxb_config / luxb_stats_t / luxb_device_view
+ABI_VERSION = 3  # must equal luxb_abi_version(): layout of luxb_config / luxb_stats_t / luxb_device_view
 
 
 def load_library():
@@ -132,18 +133,18 @@ class LuxGraph:
 
     # ---- constructors -------------------------------------------------------------------------------------
     @staticmethod
-    def _cfg(app, rank, nranks, device, start, exchange, verbose, zero_copy=False):
-        return _Config(app, rank, nranks, device, start, exchange, 1 if verbose else 0, 1 if zero_copy else 0)
+    def _cfg(app, rank, nranks, device, start, exchange, verbose, zero_copy=False, balanced=False):
+        return _Config(app, rank, nranks, device, start, exchange, 1 if verbose else 0, 1 if balanced else 0, 1 if zero_copy else 0)
 
     @classmethod
     def from_csc(cls, row_end, src, weight=None, app=APP_PAGERANK, rank=0, nranks=1, device=0, start=0,
-                 exchange=EXCHANGE_NCCL, verbose=False, zero_copy=False):
+                 exchange=EXCHANGE_NCCL, verbose=False, zero_copy=False, balanced=False):
         row_end = np.ascontiguousarray(row_end, np.uint64)
         src = np.ascontiguousarray(src, np.uint32)
         if weight is not None:
             weight = np.ascontiguousarray(weight, np.int32)
         csc = _Csc(len(row_end), len(src), _p(row_end), _p(src) if len(src) else None, _p(weight))
-        cfg = cls._cfg(app, rank, nranks, device, start, exchange, verbose, zero_copy)
+        cfg = cls._cfg(app, rank, nranks, device, start, exchange, verbose, zero_copy, balanced)
         h = C.c_void_p()
         _chk(load_library().luxb_open_csc(C.byref(csc), C.byref(cfg), C.byref(h)), "luxb_open_csc")
         return cls(h, app, rank, nranks)
@@ -158,16 +159,16 @@ class LuxGraph:
 
     @classmethod
     def from_rmat(cls, scale, nv, ne, seed, app=APP_PAGERANK, rank=0, nranks=1, device=0, start=0,
-                  exchange=EXCHANGE_NCCL, verbose=False, zero_copy=False):
-        cfg = cls._cfg(app, rank, nranks, device, start, exchange, verbose, zero_copy)
+                  exchange=EXCHANGE_NCCL, verbose=False, zero_copy=False, balanced=False):
+        cfg = cls._cfg(app, rank, nranks, device, start, exchange, verbose, zero_copy, balanced)
         h = C.c_void_p()
         _chk(load_library().luxb_open_rmat(C.c_int(scale), C.c_uint32(nv), C.c_uint64(ne), C.c_uint64(seed),
                                            C.byref(cfg), C.byref(h)), "luxb_open_rmat")
         return cls(h, app, rank, nranks)
 
     @classmethod
-    def from_bipartite(cls, users, items, ratings, seed, rank=0, nranks=1, device=0, exchange=EXCHANGE_NCCL):
-        cfg = cls._cfg(APP_COLFILTER, rank, nranks, device, 0, exchange, False)
+    def from_bipartite(cls, users, items, ratings, seed, rank=0, nranks=1, device=0, exchange=EXCHANGE_NCCL, balanced=False):
+        cfg = cls._cfg(APP_COLFILTER, rank, nranks, device, 0, exchange, False, False, balanced)
         h = C.c_void_p()
         _chk(load_library().luxb_open_bipartite(C.c_uint32(users), C.c_uint32(items), C.c_uint64(ratings),
                                                 C.c_uint64(seed), C.byref(cfg), C.byref(h)), "luxb_open_bipartite")
@@ -181,6 +182,13 @@ class LuxGraph:
         found = _chk(load_library().luxb_partition_bounds(self._h, _p(rl), _p(rr), _p(cl), _p(fl), _p(fr)),
                      "luxb_partition_bounds")
         return dict(found=found, row_left=rl, row_right=rr, col_left=cl, fq_left=fl, fq_right=fr)
+
+    def work_bounds(self):
+        """The split the ranks work on (== bounds() unless opened with balanced=True)."""
+        P = self.nranks
+        rl, rr, cl = np.zeros(P, np.uint32), np.zeros(P, np.uint32), np.zeros(P, np.uint64)
+        bal = _chk(load_library().luxb_work_bounds(self._h, _p(rl), _p(rr), _p(cl)), "luxb_work_bounds")
+        return dict(balanced=bool(bal), row_left=rl, row_right=rr, col_left=cl)
 
     # ---- communicator -------------------------------------------------------------------------------------
     @staticmethod

@@ -137,6 +137,37 @@ static int host_partition(uint32_t nv, uint64_t ne, const uint64_t* row_end, int
   return found;
 }
 
+// ---- cost-balanced work split (cfg.balanced_split, pull apps) ------------------------------------------------------
+// The reference's split balances EDGES; the sweep's cost per edge is not uniform (measured at RMAT-27: an edge into a
+// hub destination mostly travels through the shared-memory panel, ~1.5-2 ns; any other edge goes through L1, ~3.5 ns;
+// every vertex costs ~8 ns of bookkeeping — at 2 GPUs the reference split leaves the ranks 25 % apart, at 8 GPUs rank 7
+// owns 40 % of the vertices).  Contiguous destination ranges are kept; only the cut points move.  Weights in integer
+// units: vertex 16, edge into a hub (in-degree >= kBalanceHubIndeg) 4, other edge 7.
+static constexpr uint32_t kBalanceHubIndeg = 64;
+static inline uint64_t vertex_cost(uint64_t indeg) { return 16 + (indeg >= kBalanceHubIndeg ? 4 : 7) * indeg; }
+
+static void host_balanced_partition(uint32_t nv, uint64_t ne, const uint64_t* row_end, int P, uint32_t* rl, uint32_t* np, uint64_t* cl) {
+  uint64_t total = 0;
+  for (uint32_t v = 0; v < nv; ++v) total += vertex_cost(row_end[v] - (v ? row_end[v - 1] : 0));
+  uint64_t run = 0;
+  uint32_t left = 0;
+  int p = 0;
+  for (uint32_t v = 0; v < nv && p < P - 1; ++v) {
+    run += vertex_cost(row_end[v] - (v ? row_end[v - 1] : 0));
+    if (run * P >= total * (uint64_t)(p + 1)) {  // close partition p at v (inclusive)
+      rl[p] = left; np[p] = v - left + 1; cl[p] = left ? row_end[left - 1] : 0;
+      left = v + 1;
+      ++p;
+    }
+  }
+  rl[p] = left; np[p] = nv - left; cl[p] = left ? row_end[left - 1] : 0;
+  for (++p; p < P; ++p) { rl[p] = nv; np[p] = 0; cl[p] = ne; }
+}
+
+static bool use_balanced_split(const luxb_config* cfg) {
+  return cfg->balanced_split && cfg->nranks > 1 && (cfg->app == LUXB_PAGERANK || cfg->app == LUXB_COLFILTER);
+}
+
 static int check_config(const luxb_config* cfg) {
   LUXB_ARG(cfg != nullptr, "config is NULL");
   LUXB_ARG(cfg->app >= LUXB_PAGERANK && cfg->app <= LUXB_COLFILTER, "unknown app %d", (int)cfg->app);
@@ -169,6 +200,7 @@ static int graph_begin(const luxb_config* cfg, luxb_graph** out) {
   if (const char* env = getenv("LUXB_PULL_CTAS")) g->pull_ctas = std::max(1, atoi(env));
   if (const char* env = getenv("LUXB_PHASE_TIMING")) g->pt.on = atoi(env) != 0;
   if (const char* env = getenv("LUXB_L2_HINTS")) g->l2_hints = atoi(env);
+  if (const char* env = getenv("LUXB_PANEL_RESERVE_SMS")) g->panel_reserve_sms = std::max(0, atoi(env));
   return 0;
 }
 
@@ -271,7 +303,7 @@ extern "C" {
 
 const char* luxb_last_error(void) { return g_err; }
 const char* luxb_version(void) { return "lux_b200 0.2 (sm_100a)"; }
-int luxb_abi_version(void) { return 2; }
+int luxb_abi_version(void) { return 3; }
 
 int luxb_partition_csc(luxb_vid nv, luxb_eid ne, const luxb_eid* row_end, int P, luxb_vid* row_left, luxb_vid* row_right,
                        luxb_eid* col_left) {
@@ -295,7 +327,9 @@ int luxb_open_csc(const luxb_csc* csc, const luxb_config* cfg, luxb_graph** out)
   g->nv = csc->nv;
   g->ne = csc->ne;
   g->weighted = cfg->app == LUXB_COLFILTER;
-  g->parts_found = host_partition(g->nv, g->ne, csc->row_end, g->P, g->rl, g->np, g->cl);
+  g->parts_found = host_partition(g->nv, g->ne, csc->row_end, g->P, g->ref_rl, g->ref_np, g->ref_cl);
+  if (use_balanced_split(cfg)) host_balanced_partition(g->nv, g->ne, csc->row_end, g->P, g->rl, g->np, g->cl);
+  else for (int p = 0; p < g->P; ++p) { g->rl[p] = g->ref_rl[p]; g->np[p] = g->ref_np[p]; g->cl[p] = g->ref_cl[p]; }
   set_partition_derived(g);
   rc = upload_slice(g, csc->row_end + (g->n_part ? g->row_left : 0), csc->src + g->col_left,
                     g->weighted ? csc->weight + g->col_left : nullptr);
@@ -326,7 +360,9 @@ int luxb_open_file(const char* path, const luxb_config* cfg, luxb_graph** out) {
   g->nv = nv;
   g->ne = ne;
   g->weighted = cfg->app == LUXB_COLFILTER;
-  g->parts_found = host_partition(nv, ne, row_end.data(), g->P, g->rl, g->np, g->cl);
+  g->parts_found = host_partition(nv, ne, row_end.data(), g->P, g->ref_rl, g->ref_np, g->ref_cl);
+  if (use_balanced_split(cfg)) host_balanced_partition(nv, ne, row_end.data(), g->P, g->rl, g->np, g->cl);
+  else for (int p = 0; p < g->P; ++p) { g->rl[p] = g->ref_rl[p]; g->np[p] = g->ref_np[p]; g->cl[p] = g->ref_cl[p]; }
   set_partition_derived(g);
   // this rank's slice only — same seeks as pull_load_task_impl (pull_model.inl:294-318)
   std::vector<uint32_t> src(g->e_part ? g->e_part : 1);
@@ -433,11 +469,31 @@ static int open_generated(const GenSpec& spec, const luxb_config* cfg, luxb_grap
   if ((rc = dmalloc(&d_cl, LUXB_MAX_PARTS))) return fail(rc);
   if ((rc = dmalloc(&d_cnt, 1))) return fail(rc);
   partition_kernel<<<1, 1, 0, g->stream>>>(d_row_end_g, spec.nv, spec.ne, g->P, d_pt, d_pt + LUXB_MAX_PARTS, d_cl, d_cnt);
-  GEN_CUDA(cudaMemcpyAsync(g->rl, d_pt, g->P * 4, cudaMemcpyDeviceToHost, g->stream));
-  GEN_CUDA(cudaMemcpyAsync(g->np, d_pt + LUXB_MAX_PARTS, g->P * 4, cudaMemcpyDeviceToHost, g->stream));
-  GEN_CUDA(cudaMemcpyAsync(g->cl, d_cl, g->P * 8, cudaMemcpyDeviceToHost, g->stream));
+  GEN_CUDA(cudaMemcpyAsync(g->ref_rl, d_pt, g->P * 4, cudaMemcpyDeviceToHost, g->stream));
+  GEN_CUDA(cudaMemcpyAsync(g->ref_np, d_pt + LUXB_MAX_PARTS, g->P * 4, cudaMemcpyDeviceToHost, g->stream));
+  GEN_CUDA(cudaMemcpyAsync(g->ref_cl, d_cl, g->P * 8, cudaMemcpyDeviceToHost, g->stream));
   GEN_CUDA(cudaMemcpyAsync(&g->parts_found, d_cnt, 4, cudaMemcpyDeviceToHost, g->stream));
   GEN_CUDA(cudaStreamSynchronize(g->stream));
+  if (use_balanced_split(cfg)) {
+    // cost prefix over all vertices (in place of the in-degree scratch), then P - 1 binary searches for the cut points
+    uint64_t* d_cost = nullptr;
+    if ((rc = dmalloc(&d_cost, (uint64_t)spec.nv + 1))) return fail(rc);
+    vertex_cost_kernel<<<gen_grid, 256, 0, g->stream>>>(d_row_end_g, spec.nv, kBalanceHubIndeg, d_cost);
+    size_t tb2 = 0;
+    GEN_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb2, d_cost, d_cost, (int)spec.nv, g->stream));
+    void* d_tmp2 = nullptr;
+    GEN_CUDA(cudaMalloc(&d_tmp2, tb2 + 256));
+    GEN_CUDA(cub::DeviceScan::InclusiveSum(d_tmp2, tb2, d_cost, d_cost, (int)spec.nv, g->stream));
+    balanced_cut_kernel<<<1, 1, 0, g->stream>>>(d_cost, d_row_end_g, spec.nv, spec.ne, g->P, d_pt, d_pt + LUXB_MAX_PARTS, d_cl);
+    GEN_CUDA(cudaMemcpyAsync(g->rl, d_pt, g->P * 4, cudaMemcpyDeviceToHost, g->stream));
+    GEN_CUDA(cudaMemcpyAsync(g->np, d_pt + LUXB_MAX_PARTS, g->P * 4, cudaMemcpyDeviceToHost, g->stream));
+    GEN_CUDA(cudaMemcpyAsync(g->cl, d_cl, g->P * 8, cudaMemcpyDeviceToHost, g->stream));
+    GEN_CUDA(cudaStreamSynchronize(g->stream));
+    GEN_CUDA(cudaFree(d_tmp2));
+    GEN_CUDA(cudaFree(d_cost));
+  } else {
+    for (int p = 0; p < g->P; ++p) { g->rl[p] = g->ref_rl[p]; g->np[p] = g->ref_np[p]; g->cl[p] = g->ref_cl[p]; }
+  }
   set_partition_derived(g);
   // 3. local row_end (relative + sentinels)
   if ((rc = dmalloc(&g->d_row_end, (uint64_t)g->n_part + 4))) return fail(rc);
@@ -529,16 +585,27 @@ int luxb_partition_bounds(const luxb_graph* g, luxb_vid* row_left, luxb_vid* row
                           uint64_t* fq_left, uint64_t* fq_right) {
   LUXB_ARG(g != nullptr, "graph is NULL");
   uint64_t fsize = 0;
-  for (int p = 0; p < g->P; ++p) {
-    if (row_left) row_left[p] = g->rl[p];
-    if (row_right) row_right[p] = g->rl[p] + g->np[p] - 1;
-    if (col_left) col_left[p] = g->cl[p];
-    uint64_t bytes = 8 + (uint64_t)g->cap[p] * 4;  // sizeof(FrontierHeader) + mySlots * sizeof(V_ID)
+  for (int p = 0; p < g->P; ++p) {  // always the reference's split (Graph::Graph, pull_model.inl:108-131)
+    if (row_left) row_left[p] = g->ref_rl[p];
+    if (row_right) row_right[p] = g->ref_rl[p] + g->ref_np[p] - 1;
+    if (col_left) col_left[p] = g->ref_cl[p];
+    const uint32_t span = g->ref_np[p] ? g->ref_np[p] - 1 : 0;
+    uint64_t bytes = 8 + (uint64_t)(span / 16 + 100) * 4;  // sizeof(FrontierHeader) + mySlots * sizeof(V_ID), push_model.inl:393
     if (fq_left) fq_left[p] = fsize;
     fsize += bytes;
     if (fq_right) fq_right[p] = fsize - 1;
   }
   return g->parts_found;
+}
+
+int luxb_work_bounds(const luxb_graph* g, luxb_vid* row_left, luxb_vid* row_right, luxb_eid* col_left) {
+  LUXB_ARG(g != nullptr, "graph is NULL");
+  for (int p = 0; p < g->P; ++p) {
+    if (row_left) row_left[p] = g->rl[p];
+    if (row_right) row_right[p] = g->rl[p] + g->np[p] - 1;
+    if (col_left) col_left[p] = g->cl[p];
+  }
+  return use_balanced_split(&g->cfg) ? 1 : 0;
 }
 
 // ---- communicator ------------------------------------------------------------------------------------------
@@ -1534,10 +1601,14 @@ extern "C++" {
 template <class Prog, class Shape>
 static int launch_seg_shape(luxb_graph* g, const SegArgs<Prog>& a, int ctas_per_sm) {
   auto kern = seg_tile_kernel<Prog, Shape>;
+  // The panel kernel holds one persistent CTA with ~all of the shared memory on every SM it runs on; when the cold half
+  // of the exchange is in flight on the second stream (several ranks), a few SMs are left to NCCL's channel CTAs —
+  // otherwise the collective could only start once the panel kernel has finished.
+  const int reserve = (Shape::kPanel && g->packed) ? g->panel_reserve_sms : 0;
   LUXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Shape::kSmemBytes));
   int carve_pct = (int)std::min<size_t>(100, (ctas_per_sm * (Shape::kSmemBytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
   LUXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve_pct));
-  const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)g->num_sms * ctas_per_sm, a.n_stages);
+  const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)std::max(g->num_sms - reserve, 1) * ctas_per_sm, a.n_stages);
   kern<<<grid, Shape::kThreads, Shape::kSmemBytes, g->stream>>>(a);
   LUXB_CUDA(cudaGetLastError());
   return 0;

@@ -154,6 +154,37 @@ __global__ void partition_kernel(const uint64_t* __restrict__ row_end, uint32_t 
   for (int p = count; p < P; ++p) { row_left[p] = nv; n_part[p] = 0; col_left[p] = ne; }
 }
 
+// cost-balanced work split (api.cu: vertex_cost): per-vertex cost, and the cut points on its inclusive prefix
+__global__ void vertex_cost_kernel(const uint64_t* __restrict__ row_end, uint32_t nv, uint32_t hub_indeg, uint64_t* __restrict__ cost) {
+  for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t d = row_end[v] - (v ? row_end[v - 1] : 0);
+    cost[v] = 16 + (d >= hub_indeg ? 4 : 7) * d;
+  }
+}
+__global__ void balanced_cut_kernel(const uint64_t* __restrict__ cost_prefix, const uint64_t* __restrict__ row_end, uint32_t nv, uint64_t ne,
+                                    int P, uint32_t* row_left, uint32_t* n_part, uint64_t* col_left) {
+  if (blockIdx.x || threadIdx.x) return;
+  const uint64_t total = cost_prefix[nv - 1];
+  uint32_t left = 0;
+  int p = 0;
+  for (; p < P - 1 && left < nv; ++p) {
+    // smallest v >= left with prefix[v] * P >= total * (p + 1)  (same rule as host_balanced_partition)
+    uint32_t lo = left, hi = nv - 1;
+    while (lo < hi) {
+      const uint32_t mid = lo + (hi - lo) / 2;
+      if (cost_prefix[mid] * (uint64_t)P >= total * (uint64_t)(p + 1)) hi = mid; else lo = mid + 1;
+    }
+    row_left[p] = left; n_part[p] = lo - left + 1; col_left[p] = left ? row_end[left - 1] : 0;
+    left = lo + 1;
+  }
+  if (left < nv || p == P - 1) {
+    row_left[p] = left < nv ? left : nv; n_part[p] = left < nv ? nv - left : 0;
+    col_left[p] = left < nv ? (left ? row_end[left - 1] : 0) : ne;
+    ++p;
+  }
+  for (; p < P; ++p) { row_left[p] = nv; n_part[p] = 0; col_left[p] = ne; }
+}
+
 __global__ void widen_u32_to_u64_kernel(const uint32_t* __restrict__ in, uint64_t* __restrict__ out, uint64_t n) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = in[i];
 }

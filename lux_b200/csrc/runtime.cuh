@@ -52,6 +52,11 @@ struct luxb_graph {
   bool weighted = false;
 
   // global partition table (Graph::rowLeft/rowRight, core/graph.h:62)
+  // the reference's split as reported by luxb_partition_bounds; rl / np / cl below are the WORK split in use (the same
+  // unless cfg.balanced_split)
+  uint32_t ref_rl[LUXB_MAX_PARTS]{};
+  uint32_t ref_np[LUXB_MAX_PARTS]{};
+  uint64_t ref_cl[LUXB_MAX_PARTS]{};
   uint32_t rl[LUXB_MAX_PARTS]{};
   uint32_t np[LUXB_MAX_PARTS]{};
   uint64_t cl[LUXB_MAX_PARTS]{};
@@ -156,6 +161,7 @@ struct luxb_graph {
 
   // launch configuration resolved once at open time (no getenv / function-static state on the hot path)
   int pull_ctas = 3;
+  int panel_reserve_sms = 12;  // SMs the panel kernel leaves to the overlapped collective on several ranks
   int l2_hints = 1;   // LUXB_L2_HINTS: per-gather L2 eviction policies in the L1 sweep (hot evict_last, cold evict_first)
   PhaseTimer pt;
 

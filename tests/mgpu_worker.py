@@ -67,6 +67,27 @@ def main():
         dist.barrier()
     os.environ["LUXB_SB"] = "0"
 
+    # cost-balanced work split (cfg.balanced_split): other cut points, same answers; the reference's split is still reported
+    for opener, oname in ((lambda: L.LuxGraph.from_rmat(scale, nv, ne, seed, rank=rank, nranks=world, device=local, exchange=L.EXCHANGE_P2P,
+                                                       balanced=True), "rmat"),
+                          (lambda: L.LuxGraph.from_csc(row_end, src, rank=rank, nranks=world, device=local, exchange=L.EXCHANGE_P2P,
+                                                      balanced=True), "csc")):
+        g = opener()
+        b, w = g.bounds(), g.work_bounds()
+        report("balanced[%s]: reference split still reported" % oname, np.array_equal(b["row_left"], rl) and np.array_equal(b["row_right"], rr))
+        contiguous = w["row_left"][0] == 0 and all(int(w["row_right"][p]) + 1 == int(w["row_left"][p + 1]) for p in range(world - 1)) \
+            and int(w["row_right"][world - 1]) == nv - 1
+        report("balanced[%s]: contiguous cover, differs from the edge-balanced cuts" % oname,
+               w["balanced"] and contiguous and not np.array_equal(w["row_left"], rl), str(w["row_left"]))
+        g.comm_init_torch()
+        g.init()
+        g.p2p_connect_torch()
+        g.iterate(6)
+        err = (np.abs(g.values() - ref6) / np.abs(ref6)).max()
+        report("pagerank[balanced %s] world=%d" % (oname, world), err <= 1e-6, "max rel err %.2e" % err)
+        g.close()
+        dist.barrier()
+
     # from host CSC arrays too (every rank passes the whole graph, keeps its slice)
     g = L.LuxGraph.from_csc(row_end, src, app=L.APP_PAGERANK, rank=rank, nranks=world, device=local)
     g.comm_init_torch()
