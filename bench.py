@@ -336,8 +336,8 @@ def main():
                 "traffic": None, "kernel": sweep_kernel, "avg_launch_ms": 1e3 * kern_avg_max,
                 "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
                 "note": "traffic: see profiles/ (ncu dram__bytes_read.sum + dram__bytes_write.sum)"}
-    prof = os.path.join(ROOT, "profiles", "latest_traffic.json")
-    if os.path.exists(prof) and world == 1:  # the ncu capture is of the 1-GPU launch
+    prof = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.exists(prof) and world == 1:  # ncu dram__bytes_read.sum + dram__bytes_write.sum of the 1-GPU sweep kernels
         try:
             roofline["traffic"] = json.load(open(prof)).get(workload)
         except Exception:  # noqa: BLE001

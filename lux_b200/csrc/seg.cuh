@@ -237,6 +237,14 @@ __global__ void __launch_bounds__(Shape::kThreads, Shape::kPanel ? 1 : 2) seg_ti
       }
       const uint32_t excl = incl - cnt;
       const uint32_t n_round = __shfl_sync(0xffffffffu, incl, 31);
+      // the vertices this round completes: request their ids now, they are needed only after the reduction below
+      constexpr int kPre = kV / 4;  // covers the typical number of completions per round (one per ~8 edges)
+      uint32_t vpre[kPre];
+#pragma unroll
+      for (int q = 0; q < kPre; ++q) {
+        const uint32_t li = lane + 32 * q;
+        vpre[q] = li < n_round ? __ldg(a.p.close_vtx + jbase + n_closed + li) : kDummyVtx;
+      }
       // ---- serial segmented reduction inside the lane ----
       Acc run = Prog::identity(), first_val = Prog::identity();
       uint32_t h = 0;  // heads met so far in this lane
@@ -292,14 +300,18 @@ __global__ void __launch_bounds__(Shape::kThreads, Shape::kPanel ? 1 : 2) seg_ti
       if (heads) { carry = Prog::widen(tail31); seen = true; } else { carry = Prog::wcombine(carry, Prog::widen(tail31)); }
       __syncwarp();
       // ---- update() + stores of the vertices completed in this round ----
-      for (uint32_t li = lane; li < n_round; li += 32) {
-        if (li == 0 && defer_first) continue;  // finished by the fix-up kernels (for piece 0 it is the dummy before head 0)
-        const uint32_t v = __ldg(a.p.close_vtx + jbase + n_closed + li);
-        if (v != kDummyVtx) {
-          if (kPanel) a.p.out[v] = sums[li];  // raw partial sum of a (block, hub) pair; combine_hub_kernel finishes the hub
-          else store_vertex<Prog>(a.p, v, sums[li]);
-        }
+      auto finish = [&](uint32_t li, uint32_t v) {
+        if (li == 0 && defer_first) return;  // finished by the fix-up kernels (for piece 0 it is the dummy before head 0)
+        if (v == kDummyVtx) return;
+        if (kPanel) a.p.out[v] = sums[li];   // raw partial sum of a (block, hub) pair; combine_hub_kernel finishes the hub
+        else store_vertex<Prog>(a.p, v, sums[li]);
+      };
+#pragma unroll
+      for (int q = 0; q < kPre; ++q) {
+        const uint32_t li = lane + 32 * q;
+        if (li < n_round) finish(li, vpre[q]);
       }
+      for (uint32_t li = lane + 32 * kPre; li < n_round; li += 32) finish(li, __ldg(a.p.close_vtx + jbase + n_closed + li));
       n_closed += n_round;
       __syncwarp();
     }

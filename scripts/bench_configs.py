@@ -17,6 +17,10 @@ import lux_b200 as L  # noqa: E402
 
 which = sys.argv[1].split(",") if len(sys.argv) > 1 else ["C1", "C3", "C4", "C5"]
 out = []
+try:
+    PEAK = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:  # noqa: BLE001
+    PEAK = 6650.0  # B200_PROFILING.md fallback
 
 
 def scale_of(nv):
@@ -44,7 +48,9 @@ if "C1" in which:
     lhs = ((y.astype(np.float64) * np.maximum(deg, 1) - init) / 0.15).sum()
     rhs = (x.astype(np.float64) * deg).sum()
     out.append(dict(config="C1 pagerank indochina-scale", nv=nv, ne=ne, iters=10, ms_per_iter=1e3 * t / 10,
-                    MTEPS=ne * 10 / t / 1e6, linearity_checksum_rel_err=abs(lhs - rhs) / abs(rhs)))
+                    MTEPS=ne * 10 / t / 1e6, linearity_checksum_rel_err=abs(lhs - rhs) / abs(rhs),
+                    roofline=dict(bound="hbm", algorithmic_bytes_per_iter=8 * ne + 16 * nv, achieved_GBps=(8 * ne + 16 * nv) * 10 / t / 1e9,
+                                  peak_GBps=PEAK, frac=(8 * ne + 16 * nv) * 10 / t / 1e9 / PEAK, note="whole iteration, SURVEY 8d bytes")))
     print(json.dumps(out[-1]), flush=True)
 
 for tag, app, nv, ne, seed, name in (("C3", L.APP_CC, 41652230, 1468365182, 3, "C3 components twitter-scale"),
@@ -76,8 +82,15 @@ if "C5" in which:
         x = g.values()
     t = s1["loop_seconds"] - s0["loop_seconds"]
     ne = 2 * ratings
-    out.append(dict(config="C5 colfilter netflix-scale", nv=users + items, ne=ne, iters=10, ms_per_iter=1e3 * t / 10,
-                    MTEPS=ne * 10 / t / 1e6, finite=bool(np.isfinite(x).all()), mean_abs=float(np.abs(x).mean())))
+    nvv = users + items
+    out.append(dict(config="C5 colfilter netflix-scale", nv=nvv, ne=ne, iters=10, ms_per_iter=1e3 * t / 10,
+                    MTEPS=ne * 10 / t / 1e6, finite=bool(np.isfinite(x).all()), mean_abs=float(np.abs(x).mean()),
+                    roofline=dict(bound="hbm", algorithmic_bytes_per_iter=8 * ne + 168 * nvv, achieved_GBps=(8 * ne + 168 * nvv) * 10 / t / 1e9,
+                                  peak_GBps=PEAK, frac=(8 * ne + 168 * nvv) * 10 / t / 1e9 / PEAK,
+                                  l2_gather_bytes_per_iter=80 * ne, l2_gather_GBps=80 * ne * 10 / t / 1e9,
+                                  note="secondary bound (SURVEY 8d): the 80-byte vector gathers are 3 L1 sector requests each = "
+                                       "%.0f M sectors per iteration; at the measured 290 G sectors/s wall that is %.2f ms" % (
+                                           3 * ne / 1e6, 3 * ne / 290e9 * 1e3))))
     print(json.dumps(out[-1]), flush=True)
 
 os.makedirs("gpurun_out", exist_ok=True)
