@@ -200,6 +200,7 @@ static int graph_begin(const luxb_config* cfg, luxb_graph** out) {
   if (const char* env = getenv("LUXB_PULL_CTAS")) g->pull_ctas = std::max(1, atoi(env));
   if (const char* env = getenv("LUXB_PHASE_TIMING")) g->pt.on = atoi(env) != 0;
   if (const char* env = getenv("LUXB_L2_HINTS")) g->l2_hints = atoi(env);
+  if (const char* env = getenv("LUXB_FUSED_FIXUP")) g->fused_fixup = atoi(env) != 0;
   if (const char* env = getenv("LUXB_PANEL_RESERVE_SMS")) g->panel_reserve_sms = std::max(0, atoi(env));
   return 0;
 }
@@ -872,6 +873,7 @@ static int set_l2_persisting_window(luxb_graph* g, void* base, size_t bytes) {
   LUXB_CUDA(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, g->cfg.device));
   LUXB_CUDA(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, g->cfg.device));
   if (max_persist <= 0 || max_window <= 0) return 0;
+  if (const char* env = getenv("LUXB_L2_WINDOW_MB")) bytes = std::min<size_t>(bytes, (size_t)(atof(env) * 1e6));  // hottest prefix only
   size_t persist = std::min<size_t>((size_t)max_persist, bytes);
   LUXB_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist));
   cudaStreamAttrValue attr{};
@@ -1149,9 +1151,9 @@ static int p2p_barrier(luxb_graph* g) {
 }
 
 extern "C++" {
-// the partition's own CSC as a layout view (no ownership)
-static PullLayout base_layout(const luxb_graph* g, const uint32_t* src_idx) {
-  PullLayout L;
+// the partition's own CSC as a layout view (it owns nothing but the fused fix-up's chain state)
+static PullLayout& base_layout(luxb_graph* g, const uint32_t* src_idx) {
+  PullLayout& L = g->base_view;
   L.d_row_end = g->d_row_end;
   L.d_row_end32 = g->d_row_end32;
   L.d_src = const_cast<uint32_t*>(src_idx);
@@ -1216,9 +1218,31 @@ static void fill_fixup_args(PullArgs<Prog>& a, const PullLayout& L) {
   a.block_flag = L.d_block_flag;
 }
 
+// L is the layout's own descriptor (the fused fix-up keeps its launch epoch there)
 template <class Prog>
-static int launch_fixup(luxb_graph* g, const PullArgs<Prog>& a, const PullLayout& L) {
+static int launch_fixup(luxb_graph* g, const PullArgs<Prog>& a, PullLayout& L) {
   if (L.n_tiles <= 1) return 0;
+  if (g->fused_fixup) {
+    if (!L.d_chain) {
+      LUXB_TRY(dmalloc(&L.d_chain, 4ull * L.n_fix_blocks + 4));  // values, status words, [4 n] = ticket counter
+      LUXB_CUDA(cudaMemsetAsync(L.d_chain, 0, (4ull * L.n_fix_blocks + 4) * 8, g->stream));
+      L.chain_epoch = 0;
+    }
+    FixupChain<Prog> ch;
+    ch.value = L.d_chain;
+    ch.status = L.d_chain + 2ull * L.n_fix_blocks;
+    ch.ticket = L.d_chain + 4ull * L.n_fix_blocks;
+    ch.n_blocks = L.n_fix_blocks;
+    ch.epoch = ++L.chain_epoch;
+    if (L.chain_epoch >= 0x3FFFFFF0u) {  // 30-bit epochs: start over with a clean status array
+      LUXB_CUDA(cudaMemsetAsync(L.d_chain, 0, (4ull * L.n_fix_blocks + 4) * 8, g->stream));
+      L.chain_epoch = ch.epoch = 1;
+    }
+    pull_fixup_fused_kernel<Prog><<<L.n_fix_blocks, kFixBlock, 0, g->stream>>>(a, ch);
+    LUXB_CUDA(cudaGetLastError());
+    g->stats.kernel_launches++;
+    return 0;
+  }
   pull_fixup_scan_kernel<Prog><<<L.n_fix_blocks, kFixBlock, 0, g->stream>>>(a);
   pull_fixup_blocks_kernel<Prog><<<1, 1024, 0, g->stream>>>(a, L.n_fix_blocks);
   pull_fixup_apply_kernel<Prog><<<L.n_fix_blocks, kFixBlock, 0, g->stream>>>(a);
@@ -1229,7 +1253,7 @@ static int launch_fixup(luxb_graph* g, const PullArgs<Prog>& a, const PullLayout
 
 // one pull sweep over layout L.  hub_bits != nullptr: those vertices get their raw sum (panel.cuh).
 template <class Prog>
-static int launch_pull(luxb_graph* g, const PullLayout& L, const typename Prog::Vertex* x_nat, const typename Prog::Vertex* x_cold,
+static int launch_pull(luxb_graph* g, PullLayout& L, const typename Prog::Vertex* x_nat, const typename Prog::Vertex* x_cold,
                        const typename Prog::Vertex* x_hot, uint32_t hot_n, typename Prog::Vertex* out_local,
                        const typename Prog::Params& prm, const uint32_t* hub_bits = nullptr, bool timed = true) {
   if (L.n_tiles == 0) return 0;
@@ -1289,7 +1313,7 @@ static const int kNumSegPanel = sizeof(kSegPanelInfo) / sizeof(SegShapeInfo);
 
 static void free_layout(PullLayout& L) {
   void* ptrs[] = {L.d_row_end, L.d_row_end32, L.d_src, L.d_tile_v, L.d_head, L.d_tail, L.d_carry, L.d_carry_flag, L.d_block_agg, L.d_block_flag,
-                  L.d_close, L.d_empty, L.d_empty_hub};
+                  L.d_close, L.d_empty, L.d_empty_hub, L.d_chain};
   for (void* q : ptrs) if (q) cudaFree(q);
   L = PullLayout();
 }
@@ -1628,7 +1652,7 @@ extern "C++" {
 // out_buffer >= 0 (PageRank): index of the value buffer written, for the once-per-buffer constants of edge-less vertices;
 // < 0 (labels): `out_local` already holds the old values, edge-less vertices keep them.
 template <class Prog>
-static int launch_seg_main(luxb_graph* g, const PullLayout& L, const typename Prog::Vertex* x_nat, const typename Prog::Vertex* x_cold,
+static int launch_seg_main(luxb_graph* g, PullLayout& L, const typename Prog::Vertex* x_nat, const typename Prog::Vertex* x_cold,
                            typename Prog::Vertex* out_local, int out_buffer, const typename Prog::Params& prm, const uint32_t* hub_bits) {
   SegArgs<Prog> a{};
   fill_seg_args(a, L);
@@ -1677,7 +1701,7 @@ static int sweep_seg(luxb_graph* g, const typename Prog::Vertex* x_nat, const ty
   using Acc = typename Prog::Acc;
   LUXB_TRY(kt_begin(g));
   if (g->sb_on) {
-    const PullLayout& PL = g->sb_panel;
+    PullLayout& PL = g->sb_panel;
     SegArgs<Prog> pa{};
     fill_seg_args(pa, PL);
     pa.p.x_hot = reinterpret_cast<const typename Prog::Vertex*>(g->d_hot);
@@ -2380,6 +2404,7 @@ void luxb_close(luxb_graph* g) {
   }
   free_layout(g->sb_main);
   free_layout(g->sb_panel);
+  if (g->base_view.d_chain) cudaFree(g->base_view.d_chain);
   if (g->d_hub_vtx) cudaFree(g->d_hub_vtx);
   if (g->d_hub_bits) cudaFree(g->d_hub_bits);
   if (g->d_sb_partial) cudaFree(g->d_sb_partial);

@@ -461,4 +461,131 @@ __global__ void __launch_bounds__(kFixBlock) pull_fixup_apply_kernel(const __gri
   store_vertex<Prog>(a, v, Prog::narrow(totalw));
 }
 
+// ---- the same fix-up in ONE launch: chained scan with decoupled look-back -----------------------------------------------
+// Block b scans its kFixBlock tiles, publishes its aggregate, looks back over the predecessors' published aggregates /
+// inclusive prefixes (the walk stops at the first aggregate that contains a completed vertex — almost always the
+// immediate predecessor), publishes its own inclusive prefix and applies.  Publication = value word first, then a
+// status word carrying the launch's epoch (no per-launch reset of the status array).  Deterministic: the combination
+// order is the tile order whatever the scheduling.
+template <class Prog>
+struct FixupChain {
+  unsigned long long* value;   // [2 * n_blocks] aggregate / inclusive prefix values (Wide, bit-cast)
+  unsigned long long* status;  // [2 * n_blocks] (epoch << 2) | (flag << 1) | 1  for aggregate (slot 2b) / prefix (2b + 1)
+  unsigned long long* ticket;  // never reset: launch number `epoch` hands out tickets (epoch - 1) * n_blocks ...
+  uint32_t epoch, n_blocks;
+};
+
+template <class Wide>
+__device__ __forceinline__ unsigned long long wide_bits(Wide w) {
+  unsigned long long u = 0;
+  memcpy(&u, &w, sizeof(Wide));
+  return u;
+}
+template <class Wide>
+__device__ __forceinline__ Wide bits_wide(unsigned long long u) {
+  Wide w;
+  memcpy(&w, &u, sizeof(Wide));
+  return w;
+}
+
+template <class Prog>
+__global__ void __launch_bounds__(kFixBlock) pull_fixup_fused_kernel(const __grid_constant__ PullArgs<Prog> a, const FixupChain<Prog> ch) {
+  using Wide = typename Prog::Wide;
+  __shared__ Wide s_v[kFixBlock / 32];
+  __shared__ uint32_t s_f[kFixBlock / 32];
+  __shared__ Wide s_pv;
+  __shared__ uint32_t s_pf;
+  __shared__ uint32_t s_b;
+  // block index = order of arrival (a ticket), so a block only ever waits for blocks that are already running
+  if (threadIdx.x == 0) s_b = (uint32_t)(atomicAdd(ch.ticket, 1ull) - (unsigned long long)(ch.epoch - 1) * ch.n_blocks);
+  __syncthreads();
+  const uint32_t b = s_b;
+  const uint32_t t = b * kFixBlock + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t f = 0;
+  Wide v = Prog::widen(Prog::identity());
+  uint32_t i0 = 0;
+  if (t < a.n_tiles) {
+    i0 = a.tile_v[t];
+    f = a.tile_v[t + 1] > i0 ? 1u : 0u;
+    v = Prog::widen(a.tail_partial[t]);
+  }
+  // in-block inclusive segmented scan
+  Wide sv = v;
+  uint32_t sf = f;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    Wide pv = __shfl_up_sync(0xffffffffu, sv, off);
+    uint32_t pf = __shfl_up_sync(0xffffffffu, sf, off);
+    if (lane >= off) seg_combine<Prog>(sf, sv, pf, pv);
+  }
+  if (lane == 31) { s_v[warp] = sv; s_f[warp] = sf; }
+  __syncthreads();
+  Wide wv = Prog::widen(Prog::identity());
+  uint32_t wf = 0;
+  for (int w = 0; w < warp; ++w) {
+    uint32_t f2 = s_f[w];
+    Wide v2 = s_v[w];
+    seg_combine<Prog>(f2, v2, wf, wv);
+    wf = f2; wv = v2;
+  }
+  Wide ev = __shfl_up_sync(0xffffffffu, sv, 1);  // exclusive in-block prefix of this tile
+  uint32_t ef = __shfl_up_sync(0xffffffffu, sf, 1);
+  if (lane == 0) { ev = Prog::widen(Prog::identity()); ef = 0; }
+  seg_combine<Prog>(ef, ev, wf, wv);
+  if (threadIdx.x == kFixBlock - 1) {
+    // block aggregate -> publish, look back, publish the inclusive prefix
+    uint32_t af = sf;
+    Wide av = sv;
+    seg_combine<Prog>(af, av, wf, wv);
+    const unsigned long long tag = (unsigned long long)ch.epoch << 2;
+    volatile unsigned long long* st = ch.status;
+    volatile unsigned long long* va = ch.value;
+    va[2 * b] = wide_bits<Wide>(av);
+    __threadfence();
+    st[2 * b] = tag | (af << 1) | 1ull;
+    uint32_t pf = 0;
+    Wide pv = Prog::widen(Prog::identity());
+    for (int64_t q = (int64_t)b - 1; q >= 0 && !pf; --q) {
+      unsigned long long s_pre, s_agg;
+      do {  // wait for the predecessor to publish something in this epoch
+        s_pre = st[2 * q + 1];
+        s_agg = st[2 * q];
+      } while ((s_pre >> 2) != ch.epoch && (s_agg >> 2) != ch.epoch);
+      __threadfence();
+      const bool have_prefix = (s_pre >> 2) == ch.epoch;
+      uint32_t qf = (uint32_t)(((have_prefix ? s_pre : s_agg) >> 1) & 1ull);
+      Wide qv = bits_wide<Wide>(va[2 * q + (have_prefix ? 1 : 0)]);
+      // (qf, qv) precedes (pf, pv)
+      uint32_t nf = pf;
+      Wide nv_ = pv;
+      seg_combine<Prog>(nf, nv_, qf, qv);
+      pf = nf; pv = nv_;
+      if (have_prefix) break;
+    }
+    // inclusive prefix of this block = exclusive prefix (pf, pv) then aggregate (af, av)
+    uint32_t inf = af;
+    Wide inv = av;
+    seg_combine<Prog>(inf, inv, pf, pv);
+    va[2 * b + 1] = wide_bits<Wide>(inv);
+    __threadfence();
+    st[2 * b + 1] = tag | (inf << 1) | 1ull;
+    s_pv = pv;
+    s_pf = pf;
+  }
+  __syncthreads();
+  if (t == 0 || t >= a.n_tiles || !f) return;
+  // carry into this tile = block prefix then in-block exclusive prefix
+  Wide c = ev;
+  uint32_t cf = ef;
+  seg_combine<Prog>(cf, c, s_pf, s_pv);
+  const Wide totalw = Prog::wcombine(c, Prog::widen(a.head_partial[t]));
+  uint32_t vtx = i0;
+  if (a.close_vtx) {
+    vtx = a.close_vtx[i0];
+    if (vtx == 0xFFFFFFFFu) return;
+  }
+  store_vertex<Prog>(a, vtx, Prog::narrow(totalw));
+}
+
 }  // namespace luxb

@@ -24,6 +24,8 @@ struct PullLayout {
   void* d_block_agg = nullptr;
   uint32_t* d_block_flag = nullptr;
   uint32_t n_fix_blocks = 0;
+  unsigned long long* d_chain = nullptr;  // fused fix-up: [2 * n_fix_blocks] values then [2 * n_fix_blocks] status words
+  uint32_t chain_epoch = 0;
   // flagged stream (seg.cuh): d_src holds the words, d_tile_v the heads before each piece, n_tiles the pieces
   uint32_t* d_close = nullptr;      // [1 + heads] vertex completed by each head
   uint32_t* d_empty = nullptr;      // vertices without edges in this stream that are not hubs
@@ -151,6 +153,7 @@ struct luxb_graph {
   int seg_main_shape = 0, seg_panel_shape = 0;
   bool sb_on = false;
   PullLayout sb_main, sb_panel;
+  PullLayout base_view;            // the canonical CSC seen as a layout by the merge-path sweep (pull.cuh)
   uint32_t sb_n_hub = 0, sb_n_blocks = 0, sb_bs = 0, sb_n_src = 0;
   int sb_shape = 0;
   uint32_t* d_hub_vtx = nullptr;
@@ -161,6 +164,7 @@ struct luxb_graph {
 
   // launch configuration resolved once at open time (no getenv / function-static state on the hot path)
   int pull_ctas = 3;
+  bool fused_fixup = true;  // one chained-scan launch instead of the three fix-up kernels (LUXB_FUSED_FIXUP=0: three)
   int panel_reserve_sms = 12;  // SMs the panel kernel leaves to the overlapped collective on several ranks
   int l2_hints = 1;   // LUXB_L2_HINTS: per-gather L2 eviction policies in the L1 sweep (hot evict_last, cold evict_first)
   PhaseTimer pt;
