@@ -133,3 +133,34 @@ def test_zero_copy_edge_staging_matches():
         g.init()
         g.run_to_convergence()
         assert np.array_equal(g.values(), O.label_run(O.APP_SSSP, row_end, src, start=0)["labels"])
+
+
+def test_balanced_work_split_follows_the_documented_cost_rule():
+    """cfg.balanced_split (pull apps, nranks > 1): contiguous destination ranges cut where the running cost — 16 per
+    vertex, 4 per edge into a hub (in-degree >= 64), 7 per other edge — passes k/P of the total; host path (from_csc) and
+    device path (from_rmat) must agree with this restatement, and luxb_partition_bounds must keep reporting the
+    reference's greedy split.  Opening a rank needs no communicator."""
+    scale, nv = 15, 30000
+    ne = 16 * nv
+    row_end, src = O.gen_rmat_csc(scale, nv, ne, 27)
+    indeg = np.diff(np.concatenate([[0], row_end]).astype(np.int64))
+    cost = 16 + np.where(indeg >= 64, 4, 7) * indeg
+    prefix = np.cumsum(cost)
+    for P in (2, 5, 8):
+        cuts, left = [], 0
+        for p in range(P - 1):
+            v = int(np.searchsorted(prefix * P, prefix[-1] * (p + 1), side="left"))
+            v = max(v, left)
+            cuts.append((left, v))
+            left = v + 1
+        cuts.append((left, nv - 1))
+        cnt, rl, rr, cl, _, _ = O.partition(row_end, ne, P)
+        for opener in (lambda r: L.LuxGraph.from_csc(row_end, src, rank=r, nranks=P, balanced=True),
+                       lambda r: L.LuxGraph.from_rmat(scale, nv, ne, 27, rank=r, nranks=P, balanced=True)):
+            with opener(P - 1) as g:
+                w, b = g.work_bounds(), g.bounds()
+                assert w["balanced"]
+                assert [(int(a), int(c)) for a, c in zip(w["row_left"], w["row_right"])] == cuts
+                assert np.array_equal(b["row_left"], rl) and np.array_equal(b["row_right"], rr) and np.array_equal(b["col_left"], cl)
+                lo, n = g.local_range()
+                assert (lo, lo + n - 1) == cuts[P - 1]
