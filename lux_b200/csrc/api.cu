@@ -18,7 +18,7 @@
 #include "runtime.cuh"
 
 using namespace luxb;
-static const char* const kPhaseName[8] = {"pull_tile", "fixup", "refresh", "push/exchange", "barrier", "panel", "combine", ""};
+static const char* const kPhaseName[12] = {"pull_tile", "fixup", "refresh", "rechunk", "barrier", "panel", "combine", "pack", "allgather", "", "", ""};
 static void pt_mark(luxb_graph* g, int tag) {
   PhaseTimer& pt = g->pt;
   if (!pt.on) return;
@@ -200,6 +200,7 @@ static int graph_begin(const luxb_config* cfg, luxb_graph** out) {
   if (const char* env = getenv("LUXB_PULL_CTAS")) g->pull_ctas = std::max(1, atoi(env));
   if (const char* env = getenv("LUXB_PHASE_TIMING")) g->pt.on = atoi(env) != 0;
   if (const char* env = getenv("LUXB_L2_HINTS")) g->l2_hints = atoi(env);
+  if (const char* env = getenv("LUXB_OVERLAP")) g->overlap_exchange = atoi(env) != 0;
   if (const char* env = getenv("LUXB_FUSED_FIXUP")) g->fused_fixup = atoi(env) != 0;
   if (const char* env = getenv("LUXB_PANEL_RESERVE_SMS")) g->panel_reserve_sms = std::max(0, atoi(env));
   return 0;
@@ -1778,6 +1779,7 @@ static int pagerank_publish(luxb_graph* g, float* x_new) {
     g->stats.kernel_launches++;
   }
   LUXB_CUDA(cudaEventRecord(g->ev_pack, g->stream));
+  pt_mark(g, 7);
   const bool p2p = g->p2p_ready && g->cfg.exchange != LUXB_EXCHANGE_NCCL;
   // one balanced all-gather of a region of XT: re-chunk copies into the peers' XT, barrier, ncclAllGather of equal chunks
   auto exchange_region = [&](uint64_t base, uint64_t C, uint64_t lo_own, uint64_t hi_own, const uint32_t* off, cudaStream_t st,
@@ -1790,9 +1792,12 @@ static int pagerank_publish(luxb_graph* g, float* x_new) {
           LUXB_CUDA(cudaMemcpyAsync(reinterpret_cast<float*>(g->peer_xt[1 - g->cur_xt][k]) + base + lo, XTn + base + lo, (hi - lo) * 4,
                                     cudaMemcpyDefault, st));
       }
+      if (st == g->stream) pt_mark(g, 3);
       if (!*d_sync) LUXB_TRY(dmalloc(d_sync, 4));
       LUXB_NCCL(nccl().AllReduce(*d_sync, *d_sync, 1, ncclUint32, ncclSum, comm, st));  // every re-chunk copy has landed
+      if (st == g->stream) pt_mark(g, 4);
       LUXB_NCCL(nccl().AllGather(XTn + base + me * C, XTn + base, C, ncclFloat32, comm, st));
+      if (st == g->stream) pt_mark(g, 8);
     } else {
       LUXB_NCCL(nccl().GroupStart());
       for (int p = 0; p < g->P; ++p) {
@@ -1805,17 +1810,20 @@ static int pagerank_publish(luxb_graph* g, float* x_new) {
   };
   // hot part on the compute stream: the next sweep's panel gather needs it first
   LUXB_TRY(exchange_region(0, Ch, g->hot_off[me], g->hot_off[me + 1], g->hot_off, g->stream, g->comm, &g->d_sync));
-  pt_mark(g, 3);
   hot_permute_kernel<float><<<grid_for(H, 256, grid), 256, 0, g->stream>>>((float*)g->d_hot, XTn, g->d_zperm, H);
   LUXB_CUDA(cudaGetLastError());
   g->stats.kernel_launches++;
   pt_mark(g, 2);
   // cold part on the second stream / communicator: only the next MAIN sweep reads it, so it overlaps with the next
   // sweep's panel kernel (launch_seg_main waits for ev_cold)
-  LUXB_CUDA(cudaStreamWaitEvent(g->stream2, g->ev_pack, 0));
-  LUXB_TRY(exchange_region(cold_base, Cc, g->cold_off[me], g->cold_off[me + 1], g->cold_off, g->stream2, g->comm2, &g->d_sync2));
-  LUXB_CUDA(cudaEventRecord(g->ev_cold, g->stream2));
-  g->cold_pending = true;
+  if (g->overlap_exchange) {
+    LUXB_CUDA(cudaStreamWaitEvent(g->stream2, g->ev_pack, 0));
+    LUXB_TRY(exchange_region(cold_base, Cc, g->cold_off[me], g->cold_off[me + 1], g->cold_off, g->stream2, g->comm2, &g->d_sync2));
+    LUXB_CUDA(cudaEventRecord(g->ev_cold, g->stream2));
+    g->cold_pending = true;
+  } else {  // LUXB_OVERLAP=0: the cold part follows on the compute stream and communicator
+    LUXB_TRY(exchange_region(cold_base, Cc, g->cold_off[me], g->cold_off[me + 1], g->cold_off, g->stream, g->comm, &g->d_sync));
+  }
   g->cur_xt ^= 1;
   g->replica_stale = true;
   return 0;
@@ -2379,7 +2387,7 @@ void luxb_close(luxb_graph* g) {
   if (!g) return;
   if (g->pt.on && g->pt.cnt) {
     fprintf(stderr, "[luxb rank %d] phase means over %ld iterations:", g->cfg.rank, g->pt.cnt);
-    for (int k = 0; k < 7; ++k) fprintf(stderr, " %s %.3f ms;", kPhaseName[k], g->pt.sum[k] / g->pt.cnt);
+    for (int k = 0; k < 9; ++k) fprintf(stderr, " %s %.3f ms;", kPhaseName[k], g->pt.sum[k] / g->pt.cnt);
     fprintf(stderr, "\n");
   }
   cudaSetDevice(g->cfg.device);

@@ -41,7 +41,7 @@ struct PhaseTimer {
   bool on = false;
   std::vector<cudaEvent_t> ev;
   std::vector<int> tag;
-  double sum[8] = {0};
+  double sum[12] = {0};
   long cnt = 0;
 };
 
@@ -164,6 +164,7 @@ struct luxb_graph {
 
   // launch configuration resolved once at open time (no getenv / function-static state on the hot path)
   int pull_ctas = 3;
+  bool overlap_exchange = true;  // cold half of the PageRank exchange on the second stream (LUXB_OVERLAP=0: serialised)
   bool fused_fixup = true;  // one chained-scan launch instead of the three fix-up kernels (LUXB_FUSED_FIXUP=0: three)
   int panel_reserve_sms = 12;  // SMs the panel kernel leaves to the overlapped collective on several ranks
   int l2_hints = 1;   // LUXB_L2_HINTS: per-gather L2 eviction policies in the L1 sweep (hot evict_last, cold evict_first)

@@ -79,6 +79,14 @@ def launch_list(path, out, title):
              "| kernel | launches | total ms | share | avg ms |", "|---|---|---|---|---|"]
     for name, (n, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         lines.append("| `%s` | %d | %.3f | %.1f %% | %.4f |" % (name[:90], n, ns / 1e6, 100 * ns / tot, ns / 1e6 / n))
+    # the kernels launched every iteration, as shares of an iteration (graph construction excluded)
+    it = collections.OrderedDict((k, v) for k, v in agg.items() if any(t in k for t in (
+        "seg_tile_kernel", "pull_tile_kernel", "pull_fixup", "combine_hub", "hot_refresh", "hot_permute", "empties_kernel", "pack_values")))
+    tot_it = sum(a[1] for a in it.values()) or 1
+    lines += ["", "Per-iteration kernels only (shares of one iteration's device time):", "",
+              "| kernel | launches | total ms | share of iteration | avg ms |", "|---|---|---|---|---|"]
+    for name, (n, ns) in sorted(it.items(), key=lambda kv: -kv[1][1]):
+        lines.append("| `%s` | %d | %.3f | %.1f %% | %.4f |" % (name[:110], n, ns / 1e6, 100 * ns / tot_it, ns / 1e6 / n))
     open(out, "w").write("\n".join(lines) + "\n")
 
 
