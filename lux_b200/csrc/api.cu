@@ -2386,9 +2386,15 @@ int luxb_get_local_csc(luxb_graph* g, luxb_eid* row_end_abs, luxb_vid* src, int3
 void luxb_close(luxb_graph* g) {
   if (!g) return;
   if (g->pt.on && g->pt.cnt) {
-    fprintf(stderr, "[luxb rank %d] phase means over %ld iterations:", g->cfg.rank, g->pt.cnt);
-    for (int k = 0; k < 9; ++k) fprintf(stderr, " %s %.3f ms;", kPhaseName[k], g->pt.sum[k] / g->pt.cnt);
-    fprintf(stderr, "\n");
+    char line[1024];
+    int n = snprintf(line, sizeof(line), "[luxb rank %d] phase means over %ld iterations:", g->cfg.rank, g->pt.cnt);
+    double sum = 0;
+    for (int k = 0; k < 9; ++k) {
+      n += snprintf(line + n, sizeof(line) - n, " %s %.3f ms;", kPhaseName[k], g->pt.sum[k] / g->pt.cnt);
+      sum += g->pt.sum[k] / g->pt.cnt;
+    }
+    snprintf(line + n, sizeof(line) - n, " sum %.3f ms\n", sum);
+    fputs(line, stderr);  // one write per rank: the ranks' lines do not interleave
   }
   cudaSetDevice(g->cfg.device);
   if (g->stream) cudaStreamSynchronize(g->stream);
