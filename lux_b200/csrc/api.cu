@@ -18,7 +18,7 @@
 #include "runtime.cuh"
 
 using namespace luxb;
-static const char* const kPhaseName[12] = {"pull_tile", "fixup", "refresh", "rechunk", "barrier", "panel", "combine", "pack", "allgather", "", "", ""};
+static const char* const kPhaseName[12] = {"pull_tile", "fixup", "refresh", "rechunk", "barrier", "panel", "combine", "pack+push", "pull/bcast", "", "", ""};
 static void pt_mark(luxb_graph* g, int tag) {
   PhaseTimer& pt = g->pt;
   if (!pt.on) return;
@@ -632,19 +632,7 @@ int luxb_comm_init(luxb_graph* g, const char id[LUXB_UNIQUE_ID_BYTES]) {
   ncclUniqueId uid;
   memcpy(&uid, id, LUXB_UNIQUE_ID_BYTES);
   LUXB_NCCL(nccl().CommInitRank(&g->comm, g->P, uid, g->cfg.rank));
-  // a second communicator for the part of the exchange that overlaps with compute on a second stream (operations on
-  // one communicator execute in issue order): rank 0 draws its id and ships it through the first one
-  ncclUniqueId uid2;
-  memset(&uid2, 0, sizeof(uid2));
-  if (g->cfg.rank == 0) LUXB_NCCL(nccl().GetUniqueId(&uid2));
-  char* d_id = nullptr;
-  LUXB_TRY(dmalloc(&d_id, sizeof(uid2)));
-  LUXB_CUDA(cudaMemcpyAsync(d_id, &uid2, sizeof(uid2), cudaMemcpyHostToDevice, g->stream));
-  LUXB_NCCL(nccl().Broadcast(d_id, d_id, sizeof(uid2), ncclUint8, 0, g->comm, g->stream));
-  LUXB_CUDA(cudaMemcpyAsync(&uid2, d_id, sizeof(uid2), cudaMemcpyDeviceToHost, g->stream));
-  LUXB_CUDA(cudaStreamSynchronize(g->stream));
-  LUXB_CUDA(cudaFree(d_id));
-  LUXB_NCCL(nccl().CommInitRank(&g->comm2, g->P, uid2, g->cfg.rank));
+  // second stream: the cold half of the PageRank exchange overlaps with the next sweep's panel kernel
   LUXB_CUDA(cudaStreamCreateWithFlags(&g->stream2, cudaStreamNonBlocking));
   LUXB_CUDA(cudaEventCreateWithFlags(&g->ev_pack, cudaEventDisableTiming));
   LUXB_CUDA(cudaEventCreateWithFlags(&g->ev_cold, cudaEventDisableTiming));
@@ -1772,58 +1760,81 @@ static int pagerank_publish(luxb_graph* g, float* x_new) {
   const uint32_t H = g->hot_n;
   const uint64_t Ch = g->xt_hot_chunk, Cc = g->xt_cold_chunk, cold_base = Ch * g->P;  // XT = [P hot chunks | P cold chunks]
   const uint32_t nh_me = g->hot_off[me + 1] - g->hot_off[me], nc_me = g->cold_off[me + 1] - g->cold_off[me];
-  if (nh_me + nc_me) {
-    pack_values_kernel<float><<<grid_for((uint64_t)nh_me + nc_me, 256, grid), 256, 0, g->stream>>>(
-        x_new + g->row_left, g->d_pack_list, nh_me, nc_me, XTn + g->hot_off[me], XTn + cold_base + g->cold_off[me]);
-    LUXB_CUDA(cudaGetLastError());
-    g->stats.kernel_launches++;
-  }
-  LUXB_CUDA(cudaEventRecord(g->ev_pack, g->stream));
-  pt_mark(g, 7);
   const bool p2p = g->p2p_ready && g->cfg.exchange != LUXB_EXCHANGE_NCCL;
-  // one balanced all-gather of a region of XT: re-chunk copies into the peers' XT, barrier, ncclAllGather of equal chunks
-  auto exchange_region = [&](uint64_t base, uint64_t C, uint64_t lo_own, uint64_t hi_own, const uint32_t* off, cudaStream_t st,
-                             ncclComm_t comm, uint32_t** d_sync) -> int {
-    if (p2p) {
-      for (int k = 0; k < g->P; ++k) {
-        if (k == me) continue;
-        const uint64_t lo = std::max<uint64_t>(lo_own, k * C), hi = std::min<uint64_t>(hi_own, (k + 1) * C);
-        if (lo < hi)
-          LUXB_CUDA(cudaMemcpyAsync(reinterpret_cast<float*>(g->peer_xt[1 - g->cur_xt][k]) + base + lo, XTn + base + lo, (hi - lo) * 4,
-                                    cudaMemcpyDefault, st));
-      }
-      if (st == g->stream) pt_mark(g, 3);
-      if (!*d_sync) LUXB_TRY(dmalloc(d_sync, 4));
-      LUXB_NCCL(nccl().AllReduce(*d_sync, *d_sync, 1, ncclUint32, ncclSum, comm, st));  // every re-chunk copy has landed
-      if (st == g->stream) pt_mark(g, 4);
-      LUXB_NCCL(nccl().AllGather(XTn + base + me * C, XTn + base, C, ncclFloat32, comm, st));
-      if (st == g->stream) pt_mark(g, 8);
-    } else {
-      LUXB_NCCL(nccl().GroupStart());
-      for (int p = 0; p < g->P; ++p) {
-        const uint32_t n = off[p + 1] - off[p];
-        if (n) LUXB_NCCL(nccl().Broadcast(XTn + base + off[p], XTn + base + off[p], n, ncclFloat32, p, comm, st));
-      }
-      LUXB_NCCL(nccl().GroupEnd());
+  if (p2p) {
+    // ---- balanced all-gather with three kernel launches and one 4-byte collective per iteration ----
+    // 1. pack + push: every owned entry goes straight to the rank holding its equal chunk (remote stores);
+    // 2. barrier: all pushes have landed;
+    // 3. pull: every rank copies the chunks it does not hold from their holders (peer loads) — the hot region on the
+    //    compute stream (the next sweep's panel gather needs it first), the cold region on the second stream,
+    //    overlapped with that panel kernel (only the next MAIN sweep waits for it).
+    if (nh_me + nc_me) {
+      PackPushArgs<float> pa{};
+      pa.x_local = x_new + g->row_left;
+      pa.list = g->d_pack_list;
+      pa.n_hot = nh_me;
+      pa.n_cold = nc_me;
+      pa.hot_pos0 = g->hot_off[me];
+      pa.cold_pos0 = g->cold_off[me];
+      pa.hot_chunk = Ch;
+      pa.cold_chunk = Cc;
+      pa.cold_base = cold_base;
+      for (int k = 0; k < g->P; ++k) pa.xt[k] = reinterpret_cast<float*>(g->peer_xt[1 - g->cur_xt][k]);
+      pack_push_kernel<float><<<grid_for((uint64_t)nh_me + nc_me, 256, grid), 256, 0, g->stream>>>(pa);
+      LUXB_CUDA(cudaGetLastError());
+      g->stats.kernel_launches++;
     }
-    return 0;
-  };
-  // hot part on the compute stream: the next sweep's panel gather needs it first
-  LUXB_TRY(exchange_region(0, Ch, g->hot_off[me], g->hot_off[me + 1], g->hot_off, g->stream, g->comm, &g->d_sync));
+    pt_mark(g, 7);
+    LUXB_TRY(p2p_barrier(g));
+    pt_mark(g, 4);
+    auto pull = [&](uint64_t base, uint64_t C, cudaStream_t st, int ctas) -> int {
+      ChunkPullArgs ca{};
+      ca.dst = XTn + base;
+      for (int k = 0; k < g->P; ++k) ca.src[k] = reinterpret_cast<const float*>(g->peer_xt[1 - g->cur_xt][k]) + base;
+      ca.chunk = C;
+      ca.P = g->P;
+      ca.me = me;
+      chunk_pull_kernel<<<ctas, 512, 0, st>>>(ca);
+      LUXB_CUDA(cudaGetLastError());
+      g->stats.kernel_launches++;
+      return 0;
+    };
+    if (g->overlap_exchange) {
+      LUXB_CUDA(cudaEventRecord(g->ev_pack, g->stream));  // = "barrier passed"
+      LUXB_CUDA(cudaStreamWaitEvent(g->stream2, g->ev_pack, 0));
+      // beside the panel kernel: only the SMs that kernel leaves free (launch_seg_shape)
+      LUXB_TRY(pull(cold_base, Cc, g->stream2, std::max(2 * g->panel_reserve_sms, 8)));
+      LUXB_CUDA(cudaEventRecord(g->ev_cold, g->stream2));
+      g->cold_pending = true;
+      LUXB_TRY(pull(0, Ch, g->stream, g->num_sms * 2));
+    } else {
+      LUXB_TRY(pull(0, Ch, g->stream, g->num_sms * 2));
+      LUXB_TRY(pull(cold_base, Cc, g->stream, g->num_sms * 2));
+    }
+    pt_mark(g, 8);
+  } else {
+    // NCCL only (no peer mappings): local pack, then one grouped set of in-place broadcasts per region
+    if (nh_me + nc_me) {
+      pack_values_kernel<float><<<grid_for((uint64_t)nh_me + nc_me, 256, grid), 256, 0, g->stream>>>(
+          x_new + g->row_left, g->d_pack_list, nh_me, nc_me, XTn + g->hot_off[me], XTn + cold_base + g->cold_off[me]);
+      LUXB_CUDA(cudaGetLastError());
+      g->stats.kernel_launches++;
+    }
+    pt_mark(g, 7);
+    LUXB_NCCL(nccl().GroupStart());
+    for (int p = 0; p < g->P; ++p) {
+      const uint32_t nh = g->hot_off[p + 1] - g->hot_off[p], nc = g->cold_off[p + 1] - g->cold_off[p];
+      if (nh) LUXB_NCCL(nccl().Broadcast(XTn + g->hot_off[p], XTn + g->hot_off[p], nh, ncclFloat32, p, g->comm, g->stream));
+      if (nc) LUXB_NCCL(nccl().Broadcast(XTn + cold_base + g->cold_off[p], XTn + cold_base + g->cold_off[p], nc, ncclFloat32, p, g->comm,
+                                         g->stream));
+    }
+    LUXB_NCCL(nccl().GroupEnd());
+    pt_mark(g, 8);
+  }
   hot_permute_kernel<float><<<grid_for(H, 256, grid), 256, 0, g->stream>>>((float*)g->d_hot, XTn, g->d_zperm, H);
   LUXB_CUDA(cudaGetLastError());
   g->stats.kernel_launches++;
   pt_mark(g, 2);
-  // cold part on the second stream / communicator: only the next MAIN sweep reads it, so it overlaps with the next
-  // sweep's panel kernel (launch_seg_main waits for ev_cold)
-  if (g->overlap_exchange) {
-    LUXB_CUDA(cudaStreamWaitEvent(g->stream2, g->ev_pack, 0));
-    LUXB_TRY(exchange_region(cold_base, Cc, g->cold_off[me], g->cold_off[me + 1], g->cold_off, g->stream2, g->comm2, &g->d_sync2));
-    LUXB_CUDA(cudaEventRecord(g->ev_cold, g->stream2));
-    g->cold_pending = true;
-  } else {  // LUXB_OVERLAP=0: the cold part follows on the compute stream and communicator
-    LUXB_TRY(exchange_region(cold_base, Cc, g->cold_off[me], g->cold_off[me + 1], g->cold_off, g->stream, g->comm, &g->d_sync));
-  }
   g->cur_xt ^= 1;
   g->replica_stale = true;
   return 0;
@@ -2401,12 +2412,11 @@ void luxb_close(luxb_graph* g) {
   if (g->d_hot) cudaCtxResetPersistingL2Cache();  // release the lines pinned for the hot copies
   p2p_unmap(g);
   if (g->stream2) cudaStreamSynchronize(g->stream2);
-  if (g->comm2) nccl().CommDestroy(g->comm2);
   if (g->comm) nccl().CommDestroy(g->comm);
   if (g->ev_pack) cudaEventDestroy(g->ev_pack);
   if (g->ev_cold) cudaEventDestroy(g->ev_cold);
   if (g->stream2) cudaStreamDestroy(g->stream2);
-  if (g->d_sync2) cudaFree(g->d_sync2);
+
   void* ptrs[] = {g->d_row_end, g->d_row_end32, g->d_src, g->d_weight, g->d_tile_v, g->d_head, g->d_tail, g->d_deg, g->d_val[0], g->d_val[1],
                   g->d_cur, g->d_out_end, g->d_out_dst, g->d_fq_all, g->d_fq_new, g->d_fq_tmp, g->d_hdr_all, g->d_counters,
                   g->d_chunk_first, g->d_chunk_vtx, g->d_partial, g->d_sync, g->d_hot_order, g->d_src_gather,

@@ -344,10 +344,64 @@ __global__ void pack_values_kernel(const T* __restrict__ x_local, const uint32_t
     if (k < n_hot) dst_hot[k] = v; else dst_cold[k - n_hot] = v;
   }
 }
+// step 1 of the balanced all-gather fused into the pack: every owned entry is stored straight into the transfer array of the
+// rank that HOLDS its equal chunk (remote NVLink stores, coalesced: consecutive entries sit in consecutive positions) —
+// one kernel launch instead of a local pack plus 2 (P - 1) peer cudaMemcpyAsync calls (at 8 ranks the iteration was bound
+// by the HOST issuing ~45 API calls, profiles/r02a_bench_n8_phases.txt).
+template <class T>
+struct PackPushArgs {
+  const T* x_local;        // this rank's new values, local order
+  const uint32_t* list;    // local indices of [hot owned | cold-active owned] vertices in transfer order
+  uint32_t n_hot, n_cold;
+  uint64_t hot_pos0, cold_pos0;   // position of the first owned entry inside the hot / cold region
+  uint64_t hot_chunk, cold_chunk; // equal chunk sizes (elements) of the two regions
+  uint64_t cold_base;             // offset of the cold region inside XT
+  T* xt[LUXB_MAX_PARTS];          // every rank's transfer array (own rank included)
+};
+template <class T>
+__global__ void pack_push_kernel(const __grid_constant__ PackPushArgs<T> a) {
+  const uint64_t n = (uint64_t)a.n_hot + a.n_cold;
+  for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
+    const T v = a.x_local[a.list[k]];
+    if (k < a.n_hot) {
+      const uint64_t pos = a.hot_pos0 + k;
+      a.xt[pos / a.hot_chunk][pos] = v;
+    } else {
+      const uint64_t pos = a.cold_pos0 + (k - a.n_hot);
+      a.xt[pos / a.cold_chunk][a.cold_base + pos] = v;
+    }
+  }
+}
+
 // hot part of the transfer array (owner-grouped) -> globally hotness-ordered copy
 template <class T>
 __global__ void hot_permute_kernel(T* __restrict__ hot, const T* __restrict__ xt_hot, const uint32_t* __restrict__ zperm, uint32_t H) {
   for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < H; k += (uint64_t)gridDim.x * blockDim.x) hot[zperm[k]] = xt_hot[k];
+}
+
+// step 2 of the balanced all-gather without a library collective: after the barrier every rank PULLS the equal chunks it
+// does not hold from their holders' transfer arrays over NVLink — 128-bit peer loads from all P - 1 peers concurrently
+// (64 KB slabs dealt round-robin over the peers), stores to local HBM.  Chunk k sits at offset k * chunk in every XT.
+struct ChunkPullArgs {
+  float* dst;                         // this rank's XT region
+  const float* src[LUXB_MAX_PARTS];   // every rank's XT region (peer pointers from cudaIpcOpenMemHandle)
+  uint64_t chunk;                     // elements per chunk (multiple of 32)
+  int P, me;
+};
+__global__ void __launch_bounds__(512) chunk_pull_kernel(const __grid_constant__ ChunkPullArgs a) {
+  constexpr uint64_t kSlab = 4096;  // float4 per slab
+  const uint64_t v4 = a.chunk / 4;
+  const uint64_t slabs_per_chunk = (v4 + kSlab - 1) / kSlab;
+  const uint64_t units = slabs_per_chunk * (uint64_t)(a.P - 1);
+  for (uint64_t u = blockIdx.x; u < units; u += gridDim.x) {
+    const int q = (int)(u % (uint64_t)(a.P - 1));
+    const int k = q < a.me ? q : q + 1;
+    const uint64_t j0 = (u / (uint64_t)(a.P - 1)) * kSlab;
+    const uint64_t j1 = j0 + kSlab < v4 ? j0 + kSlab : v4;
+    const float4* s = reinterpret_cast<const float4*>(a.src[k] + (uint64_t)k * a.chunk);
+    float4* d = reinterpret_cast<float4*>(a.dst + (uint64_t)k * a.chunk);
+    for (uint64_t j = j0 + threadIdx.x; j < j1; j += blockDim.x) d[j] = s[j];
+  }
 }
 
 // P2P push exchange: copy up to two contiguous regions of this rank's buffers to the same offsets of every peer's

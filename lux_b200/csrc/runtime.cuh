@@ -110,12 +110,11 @@ struct luxb_graph {
   float* d_xt[2] = {nullptr, nullptr};
   int cur_xt = 0;
   uint64_t xt_hot_chunk = 0, xt_cold_chunk = 0;  // equal chunks (elements) of the two balanced all-gathers; XT = [P hot chunks | P cold chunks]
-  // the cold part of the exchange runs on a second stream / communicator, overlapped with the next sweep's panel gather
+  // the cold part of the exchange runs on a second stream, overlapped with the next sweep's panel gather
   cudaStream_t stream2 = nullptr;
-  luxb::ncclComm_t comm2 = nullptr;
   cudaEvent_t ev_pack = nullptr, ev_cold = nullptr;
   bool cold_pending = false;                 // ev_cold has been recorded and not yet waited for by a main sweep
-  uint32_t* d_sync2 = nullptr;
+
   void* peer_xt[2][LUXB_MAX_PARTS]{};
   bool replica_stale = false;                // natural-order replica holds only this rank's slice (gathered on demand)
   // push apps
