@@ -397,7 +397,11 @@ def main():
                       "partitions_covered": world, "device_out_degrees_equal_oracle": deg_dev_ok,
                       "what": "device x_k -> one device iteration vs one oracle iteration (fp64 sums) on the sample"}
             if world == 1 and not args.no_cpu_baseline:
-                mteps, cores, times = time_oracle_sample(nv, blk_rnd, deg_o, x_k, budget_s=12.0)
+                # x_k came back from the device through one host thread (all its pages on one NUMA node): time the oracle
+                # on a copy whose pages were first touched by the OpenMP threads, like the reference arm's x0
+                x_par = O.pagerank_init(deg_o)
+                np.copyto(x_par, x_k)
+                mteps, cores, times = time_oracle_sample(nv, blk_rnd, deg_o, x_par, budget_s=12.0)
                 cpu_base = {"value": mteps, "unit": "MTEPS", "cores": cores, "kind": "port", "numa_nodes": numa_nodes(),
                             "sample": "1 PageRank iteration over %s (the reference arm's sample), median of %d runs" % (
                                 blk_rnd["desc"], len(times))}
