@@ -43,8 +43,8 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=int, default=27, help="RMAT scale (27 = BASELINE config; smaller only for debugging)")
     ap.add_argument("--edge-factor", type=int, default=16)
-    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "p2p", "p2p_fused"],
-                    help="auto = p2p: packed balanced all-gather (pack + NVLink re-chunk + ncclAllGather of equal chunks)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "p2p"],
+                    help="auto = p2p: packed balanced all-gather in three kernels (pack+push, barrier, chunk pull over NVLink)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
@@ -241,7 +241,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if args.exchange == "auto":
         args.exchange = "p2p"
-    exchange = {"p2p": L.EXCHANGE_P2P, "p2p_fused": L.EXCHANGE_P2P_FUSED, "nccl": L.EXCHANGE_NCCL}[args.exchange]
+    exchange = {"p2p": L.EXCHANGE_P2P, "nccl": L.EXCHANGE_NCCL}[args.exchange]
     t_build0 = time.perf_counter()
     g = L.LuxGraph.from_rmat(scale, nv, ne, SEED, rank=rank, nranks=world, device=local, exchange=exchange,
                              balanced=not args.reference_split)

@@ -52,11 +52,15 @@ typedef enum {
 } luxb_app;
 
 typedef enum {
-  LUXB_EXCHANGE_NCCL = 0, /* per-iteration NCCL all-gather (grouped broadcasts of unequal slices) */
-  LUXB_EXCHANGE_P2P = 1,  /* balanced all-gather: each rank DMA-copies the parts of its slice that fall into a peer's
-                             EQUAL chunk into that peer's replica (NVLink), then ncclAllGather of the equal chunks */
-  LUXB_EXCHANGE_P2P_FUSED = 2 /* the gather kernel itself stores every new value into every peer's replica (fused
-                             compute + all-gather; wins at 2 GPUs, loses at 8 where per-tile stores are tiny) */
+  LUXB_EXCHANGE_NCCL = 0, /* library collectives only: PageRank packs its share and broadcasts the two ranges of every
+                             owner (grouped ncclBroadcast); CC / SSSP broadcast frontier slots and label slices;
+                             col_filter all-gathers the vector slices.  Needs no peer mappings */
+  LUXB_EXCHANGE_P2P = 1,  /* peer memory over NVLink (luxb_p2p_export / import): PageRank = pack+push to the equal-chunk
+                             holders, 4-byte barrier, chunk pull (balanced all-gather in three kernels, cold half
+                             overlapped on a second stream); CC / SSSP = frontier P2P push into the peers' slot tables
+                             and label replicas; col_filter = peer stores of the new vectors */
+  LUXB_EXCHANGE_P2P_FUSED = 2 /* kept for source compatibility: same as LUXB_EXCHANGE_P2P (round 1's fused stores from the
+                             gather kernel lost at 8 GPUs and are gone) */
 } luxb_exchange;
 
 /* Whole-graph CSC in caller-owned host memory — the arrays of a .lux file (tools/converter.cc:98-124):

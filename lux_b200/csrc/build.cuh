@@ -404,38 +404,6 @@ __global__ void __launch_bounds__(512) chunk_pull_kernel(const __grid_constant__
   }
 }
 
-// P2P push exchange: copy up to two contiguous regions of this rank's buffers to the same offsets of every peer's
-// buffers with 128-bit stores (NVLink writes; peers' pointers come from cudaIpcOpenMemHandle).
-struct PushRegions {
-  const uint32_t* src[2];
-  uint64_t words[2];
-  uint32_t* dst[2][LUXB_MAX_PARTS];
-  int n_regions, n_peers;
-};
-__global__ void p2p_push_kernel(const __grid_constant__ PushRegions r) {
-  for (int q = 0; q < r.n_regions; ++q) {
-    const uint32_t* s = r.src[q];
-    const uint64_t n = r.words[q];
-    // head up to 16-byte alignment, body as uint4, tail
-    uint64_t head = ((16 - ((uintptr_t)s & 15)) & 15) >> 2;
-    if (head > n) head = n;
-    uint64_t body = (n - head) >> 2;
-    for (int p = 0; p < r.n_peers; ++p) {
-      uint32_t* d = r.dst[q][p];
-      if ((((uintptr_t)d) & 15) != (((uintptr_t)s) & 15)) {  // differently aligned: word copies
-        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) d[i] = s[i];
-        continue;
-      }
-      for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < head; i += (uint64_t)gridDim.x * blockDim.x) d[i] = s[i];
-      const uint4* s4 = reinterpret_cast<const uint4*>(s + head);
-      uint4* d4 = reinterpret_cast<uint4*>(d + head);
-      for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < body; i += (uint64_t)gridDim.x * blockDim.x) d4[i] = s4[i];
-      for (uint64_t i = head + body * 4 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-        d[i] = s[i];
-    }
-  }
-}
-
 // PageRank init: x0[v] = (1/nv)/deg[v], or 1/nv for deg 0  (pagerank_gpu.cu:255-259)
 __global__ void pr_init_kernel(const uint32_t* __restrict__ deg, uint32_t nv, float* __restrict__ x) {
   float rank = __fdiv_rn(1.0f, (float)nv);
