@@ -1264,7 +1264,6 @@ static int launch_pull(luxb_graph* g, PullLayout& L, const typename Prog::Vertex
   a.prm = prm;
   a.hub_bits = hub_bits;
   a.raw_out = 0;
-  a.n_peers = 0;
   if (timed) LUXB_TRY(kt_begin(g));
   switch (g->pull_shape) {
 #define LUXB_CASE_SHAPE(id, ipt, warps, stages) \
@@ -1726,7 +1725,6 @@ static int sweep_seg(luxb_graph* g, const typename Prog::Vertex* x_nat, const ty
     ca.x_nat = x_nat;
     ca.out = out_local;
     ca.prm = prm;
-    ca.n_peers = 0;
     combine_hub_kernel<Prog><<<grid_for(g->sb_n_hub, 256, g->num_sms * 8), 256, 0, g->stream>>>(ca);
     LUXB_CUDA(cudaGetLastError());
     g->stats.kernel_launches++;

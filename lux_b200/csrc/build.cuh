@@ -3,8 +3,10 @@
 // Replaces the CPU load/scan tasks and the init kernels of the reference:
 //   pull_scan_task_impl  pull_model.inl:322-345      -> hist_src_kernel
 //   init_push_kernel / init_push_row_ptrs / init_push_col_idxs components_gpu.cu:550-607 -> build_push_csr()
-//   Graph::Graph partitioner pull_model.inl:108-131  -> partition_kernel (bit-identical bounds)
-// Not on the timed hot path; device-wide scans/sorts use CUB (bundled with CUDA, as the reference itself does).
+//   Graph::Graph partitioner pull_model.inl:108-131  -> partition_kernel (bit-identical bounds); balanced_cut_kernel
+//                                                      for the optional cost-balanced work split
+// plus the hot-packed gather layout, and the kernels of PageRank's packed exchange (pack_push / chunk_pull / hot_permute:
+// those three run every iteration).  The rest is not on the timed hot path; device-wide scans/sorts use CUB (bundled with CUDA, as the reference itself does).
 #pragma once
 #include "common.cuh"
 

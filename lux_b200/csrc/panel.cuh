@@ -136,8 +136,6 @@ struct CombineArgs {
   const typename Prog::Vertex* x_nat; // natural-order values of the previous iteration (update()'s old value)
   typename Prog::Vertex* out;  // [n_part] local; holds the main kernel's RAW sum for hub vertices on entry
   typename Prog::Params prm;
-  int n_peers;
-  typename Prog::Vertex* peer_out[LUXB_MAX_PEERS];
 };
 
 template <class Prog>
@@ -151,7 +149,6 @@ __global__ void combine_hub_kernel(const __grid_constant__ CombineArgs<Prog> a) 
     const typename Prog::Vertex oldv = Prog::kNeedsOld ? a.x_nat[a.row_left + v] : typename Prog::Vertex();
     const typename Prog::Vertex nv_ = Prog::update(a.row_left + v, Prog::narrow(t), oldv, a.prm);
     a.out[v] = nv_;
-    for (int p = 0; p < a.n_peers; ++p) a.peer_out[p][v] = nv_;
   }
 }
 

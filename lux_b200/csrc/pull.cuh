@@ -1,7 +1,10 @@
-// pull.cuh — pull-model gather over a partition's CSC slice (replaces pr_kernel pagerank_gpu.cu:49-102 and
-// cc_pull_kernel / sssp_pull_kernel components_gpu.cu:85-130, sssp_gpu.cu:85-130).
+// pull.cuh — (1) the merge-path tile sweep over a partition's canonical CSC slice (replaces pr_kernel pagerank_gpu.cu:49-102
+// and cc_pull_kernel / sssp_pull_kernel components_gpu.cu:85-130, sssp_gpu.cu:85-130): round 1's kernel, kept for graphs
+// whose edge arrays stay in zero-copy host memory and as LUXB_SWEEP=merge; the default sweep is the flagged
+// segmented-scan stream of seg.cuh.  (2) What both sweeps share: PullArgs, store_vertex (update() / raw sums for hub
+// vertices), the gather loads with L1 / L2 policies, and the cross-tile FIX-UP (three kernels, or one chained scan).
 //
-// Design (B200-first, not a translation).  The partition's work list is the MERGE of its nPart vertex-end markers
+// Merge-path design (B200-first, not a translation).  The partition's work list is the MERGE of its nPart vertex-end markers
 // (row_end) and its ePart in-edges (merge-path): cut into equal WARP TILES of W = 32 * kIPT merge items, so every
 // warp gets the same amount of (vertex + edge) work no matter how skewed the in-degrees are.  Warps are completely
 // independent — there is no __syncthreads in the hot loop — so the gather phase of one warp overlaps the reduction
@@ -18,8 +21,7 @@
 //   3. the lane walks its kIPT merge items serially: complete per-vertex reductions go to the warp's sums[] slot,
 //      the leading and trailing partials are stitched across lanes by a segmented warp-shuffle scan (fixed shape ->
 //      deterministic, unlike the reference's float atomicAdd);
-//   4. a lane-strided pass applies the vertex program's update() and stores the new values coalesced — to this GPU's
-//      replica and, in P2P exchange mode, straight into every peer GPU's replica (fused compute + all-gather).
+//   4. a lane-strided pass applies the vertex program's update() and stores the new values coalesced.
 // A vertex whose in-edge list crosses warp-tile boundaries is finished by the fix-up kernels below: a segmented scan
 // over the tiles' tail partials (fp64 for PageRank) in ascending tile order, independent of the grid size.
 #pragma once
@@ -76,8 +78,6 @@ struct PullArgs {
   int l2_hints;  // gathers carry L2 eviction policies (hot: evict_last, cold: evict_first)
   // flagged segmented-scan sweep (seg.cuh): tile_v counts HEADS, and head j completes vertex close_vtx[j]
   const uint32_t* close_vtx;
-  int n_peers;                                        // P2P exchange: peers' slice pointers (local index)
-  typename Prog::Vertex* peer_out[LUXB_MAX_PEERS];
 };
 
 template <class Prog>
@@ -99,7 +99,6 @@ __device__ __forceinline__ void store_vertex(const PullArgs<Prog>& a, uint32_t v
   Vertex oldv = Prog::kNeedsOld ? __ldg(a.x_nat + a.row_left + v) : Vertex();
   Vertex nv_ = Prog::update(a.row_left + v, sum, oldv, a.prm);
   a.out[v] = nv_;
-  for (int p = 0; p < a.n_peers; ++p) a.peer_out[p][v] = nv_;
 }
 
 __global__ void tile_table_kernel(const uint64_t* __restrict__ row_end, uint32_t n_part, uint64_t e_part, uint32_t tile,
