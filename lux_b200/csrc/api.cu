@@ -142,9 +142,10 @@ static int host_partition(uint32_t nv, uint64_t ne, const uint64_t* row_end, int
 // hub destination mostly travels through the shared-memory panel, ~1.5-2 ns; any other edge goes through L1, ~3.5 ns;
 // every vertex costs ~8 ns of bookkeeping — at 2 GPUs the reference split leaves the ranks 25 % apart, at 8 GPUs rank 7
 // owns 40 % of the vertices).  Contiguous destination ranges are kept; only the cut points move.  Weights in integer
-// units: vertex 16, edge into a hub (in-degree >= kBalanceHubIndeg) 4, other edge 7.
+// units: vertex 8, edge into a hub (in-degree >= kBalanceHubIndeg) 4, other edge 7 (at 8 GPUs with vertex = 16 the
+// vertex-rich last rank finished its sweep a third earlier than rank 0: profiles/r02a_bench_n8_phases.txt).
 static constexpr uint32_t kBalanceHubIndeg = 64;
-static inline uint64_t vertex_cost(uint64_t indeg) { return 16 + (indeg >= kBalanceHubIndeg ? 4 : 7) * indeg; }
+static inline uint64_t vertex_cost(uint64_t indeg) { return 8 + (indeg >= kBalanceHubIndeg ? 4 : 7) * indeg; }
 
 static void host_balanced_partition(uint32_t nv, uint64_t ne, const uint64_t* row_end, int P, uint32_t* rl, uint32_t* np, uint64_t* cl) {
   uint64_t total = 0;

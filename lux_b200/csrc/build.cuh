@@ -160,7 +160,7 @@ __global__ void partition_kernel(const uint64_t* __restrict__ row_end, uint32_t 
 __global__ void vertex_cost_kernel(const uint64_t* __restrict__ row_end, uint32_t nv, uint32_t hub_indeg, uint64_t* __restrict__ cost) {
   for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t d = row_end[v] - (v ? row_end[v - 1] : 0);
-    cost[v] = 16 + (d >= hub_indeg ? 4 : 7) * d;
+    cost[v] = 8 + (d >= hub_indeg ? 4 : 7) * d;
   }
 }
 __global__ void balanced_cut_kernel(const uint64_t* __restrict__ cost_prefix, const uint64_t* __restrict__ row_end, uint32_t nv, uint64_t ne,

@@ -136,7 +136,7 @@ def test_zero_copy_edge_staging_matches():
 
 
 def test_balanced_work_split_follows_the_documented_cost_rule():
-    """cfg.balanced_split (pull apps, nranks > 1): contiguous destination ranges cut where the running cost — 16 per
+    """cfg.balanced_split (pull apps, nranks > 1): contiguous destination ranges cut where the running cost — 8 per
     vertex, 4 per edge into a hub (in-degree >= 64), 7 per other edge — passes k/P of the total; host path (from_csc) and
     device path (from_rmat) must agree with this restatement, and luxb_partition_bounds must keep reporting the
     reference's greedy split.  Opening a rank needs no communicator."""
@@ -144,7 +144,7 @@ def test_balanced_work_split_follows_the_documented_cost_rule():
     ne = 16 * nv
     row_end, src = O.gen_rmat_csc(scale, nv, ne, 27)
     indeg = np.diff(np.concatenate([[0], row_end]).astype(np.int64))
-    cost = 16 + np.where(indeg >= 64, 4, 7) * indeg
+    cost = 8 + np.where(indeg >= 64, 4, 7) * indeg
     prefix = np.cumsum(cost)
     for P in (2, 5, 8):
         cuts, left = [], 0
