@@ -28,6 +28,20 @@ static void pt_mark(luxb_graph* g, int tag) {
   pt.ev.push_back(e);
   pt.tag.push_back(tag);
 }
+static void pt_print(luxb_graph* g) {
+  if (g->pt.on && g->pt.cnt) {
+    char line[1024];
+    int n = snprintf(line, sizeof(line), "[luxb rank %d] phase means over %ld iterations:", g->cfg.rank, g->pt.cnt);
+    double sum = 0;
+    for (int k = 0; k < 9; ++k) {
+      n += snprintf(line + n, sizeof(line) - n, " %s %.3f ms;", kPhaseName[k], g->pt.sum[k] / g->pt.cnt);
+      sum += g->pt.sum[k] / g->pt.cnt;
+    }
+    snprintf(line + n, sizeof(line) - n, " sum %.3f ms\n", sum);
+    fputs(line, stderr);  // one write per rank: the ranks' lines do not interleave
+  }
+}
+
 static void pt_flush(luxb_graph* g) {
   PhaseTimer& pt = g->pt;
   if (!pt.on || pt.ev.empty()) return;
@@ -199,9 +213,11 @@ static int graph_begin(const luxb_config* cfg, luxb_graph** out) {
   LUXB_CUDA(cudaDeviceGetAttribute(&g->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
   g->pull_ctas = kDefaultPullCtas;
   if (const char* env = getenv("LUXB_PULL_CTAS")) g->pull_ctas = std::max(1, atoi(env));
-  if (const char* env = getenv("LUXB_PHASE_TIMING")) g->pt.on = atoi(env) != 0;
+  if (const char* env = getenv("LUXB_PHASE_TIMING")) { g->pt.on = atoi(env) != 0; g->pt.per_call = atoi(env) == 2; }
   if (const char* env = getenv("LUXB_L2_HINTS")) g->l2_hints = atoi(env);
   if (const char* env = getenv("LUXB_OVERLAP")) g->overlap_exchange = atoi(env) != 0;
+  if (const char* env = getenv("LUXB_BARRIER")) g->flag_barrier = strcmp(env, "nccl") != 0;
+  if (const char* env = getenv("LUXB_PUSH")) g->direct_push = strcmp(env, "direct") == 0;
   if (const char* env = getenv("LUXB_FUSED_FIXUP")) g->fused_fixup = atoi(env) != 0;
   if (const char* env = getenv("LUXB_PANEL_RESERVE_SMS")) g->panel_reserve_sms = std::max(0, atoi(env));
   return 0;
@@ -644,7 +660,8 @@ struct P2PBlob {
   cudaIpcMemHandle_t val[2];  // natural-order replicas (col_filter stores into its peers' replicas)
   cudaIpcMemHandle_t xt[2];   // PageRank: packed transfer arrays
   cudaIpcMemHandle_t fq;      // CC / SSSP: frontier slots of every partition (val[0] = label replica)
-  int has_val, has_xt, has_fq;
+  cudaIpcMemHandle_t flags;   // barrier flag words (flag_barrier_kernel)
+  int has_val, has_xt, has_fq, has_flags;
 };
 
 int luxb_p2p_export(luxb_graph* g, void* blob, size_t* blob_bytes) {
@@ -664,6 +681,16 @@ int luxb_p2p_export(luxb_graph* g, void* blob, size_t* blob_bytes) {
   if (g->packed) {
     for (int k = 0; k < 2; ++k) LUXB_CUDA(cudaIpcGetMemHandle(&b.xt[k], g->d_xt[k]));
     b.has_xt = 1;
+  }
+  if (g->flag_barrier) {
+    if (!g->d_flags) {
+      LUXB_TRY(dmalloc(&g->d_flags, LUXB_MAX_PARTS));
+      LUXB_CUDA(cudaMemset(g->d_flags, 0, sizeof(uint32_t) * LUXB_MAX_PARTS));  // before any peer can learn the handle
+      LUXB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g->h_barrier_err), 4, cudaHostAllocMapped));
+      *g->h_barrier_err = 0;
+    }
+    LUXB_CUDA(cudaIpcGetMemHandle(&b.flags, g->d_flags));
+    b.has_flags = 1;
   }
   memcpy(blob, &b, sizeof(b));
   *blob_bytes = sizeof(P2PBlob);
@@ -686,13 +713,25 @@ int luxb_p2p_import(luxb_graph* g, const void* all_blobs, size_t blob_bytes_each
         if (g->peer_xt[k][p]) { cudaIpcCloseMemHandle(g->peer_xt[k][p]); g->peer_xt[k][p] = nullptr; }
       }
       if (g->peer_fq[p]) { cudaIpcCloseMemHandle(g->peer_fq[p]); g->peer_fq[p] = nullptr; }
+      if (g->peer_flags[p]) { cudaIpcCloseMemHandle(g->peer_flags[p]); g->peer_flags[p] = nullptr; }
     }
   };
+  bool all_flags = g->flag_barrier && g->d_flags;
+  for (int p = 0; p < g->P; ++p) all_flags = all_flags && (p == g->cfg.rank || blobs[p].has_flags);
   for (int p = 0; p < g->P; ++p) {
     if (p == g->cfg.rank) {
       for (int k = 0; k < 2; ++k) { g->peer_val[k][p] = g->d_val[k]; g->peer_xt[k][p] = g->d_xt[k]; }
       g->peer_fq[p] = g->d_fq_all;
+      g->peer_flags[p] = g->d_flags;
       continue;
+    }
+    if (all_flags) {
+      cudaError_t e = cudaIpcOpenMemHandle(&g->peer_flags[p], blobs[p].flags, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        set_error("cudaIpcOpenMemHandle (rank %d's barrier flags): %s", p, cudaGetErrorString(e));
+        undo();
+        return LUXB_ERR_CUDA;
+      }
     }
     if (blobs[p].has_fq && g->d_fq_all) {
       cudaError_t e = cudaIpcOpenMemHandle(&g->peer_fq[p], blobs[p].fq, cudaIpcMemLazyEnablePeerAccess);
@@ -714,6 +753,7 @@ int luxb_p2p_import(luxb_graph* g, const void* all_blobs, size_t blob_bytes_each
       }
     }
   }
+  g->flag_barrier = all_flags;  // every rank decides alike: the blobs are the same everywhere
   g->p2p_ready = true;
   return 0;
 }
@@ -733,6 +773,7 @@ static void p2p_unmap(luxb_graph* g) {
       if (g->peer_xt[k][p]) { cudaIpcCloseMemHandle(g->peer_xt[k][p]); g->peer_xt[k][p] = nullptr; }
     }
     if (g->peer_fq[p]) { cudaIpcCloseMemHandle(g->peer_fq[p]); g->peer_fq[p] = nullptr; }
+    if (g->peer_flags[p]) { cudaIpcCloseMemHandle(g->peer_flags[p]); g->peer_flags[p] = nullptr; }
   }
   g->p2p_ready = false;
 }
@@ -1135,6 +1176,19 @@ static int allgather_slices(luxb_graph* g, void* replica, size_t elem_bytes) {
 // completes on a rank, every peer's kernels (and therefore their stores into this rank's replica) are done.
 static int p2p_barrier(luxb_graph* g) {
   if (g->P == 1) return 0;
+  if (g->flag_barrier && g->p2p_ready) {
+    FlagBarrierArgs a{};
+    for (int p = 0; p < g->P; ++p) a.peer[p] = reinterpret_cast<uint32_t*>(g->peer_flags[p]);
+    a.mine = g->d_flags;
+    a.err = g->h_barrier_err;
+    a.P = g->P;
+    a.me = g->cfg.rank;
+    a.epoch = ++g->barrier_epoch;
+    flag_barrier_kernel<<<1, LUXB_MAX_PARTS, 0, g->stream>>>(a);
+    LUXB_CUDA(cudaGetLastError());
+    g->stats.kernel_launches++;
+    return 0;
+  }
   if (!g->d_sync) LUXB_TRY(dmalloc(&g->d_sync, 4));
   LUXB_NCCL(nccl().AllReduce(g->d_sync, g->d_sync, 1, ncclUint32, ncclSum, g->comm, g->stream));
   return 0;
@@ -1779,7 +1833,10 @@ static int pagerank_publish(luxb_graph* g, float* x_new) {
       pa.cold_chunk = Cc;
       pa.cold_base = cold_base;
       for (int k = 0; k < g->P; ++k) pa.xt[k] = reinterpret_cast<float*>(g->peer_xt[1 - g->cur_xt][k]);
-      pack_push_kernel<float><<<grid_for((uint64_t)nh_me + nc_me, 256, grid), 256, 0, g->stream>>>(pa);
+      pa.P = g->P;
+      const int pgrid = grid_for((uint64_t)nh_me + nc_me, 256, grid);
+      if (g->direct_push) pack_push_kernel<float, true><<<pgrid, 256, 0, g->stream>>>(pa);
+      else pack_push_kernel<float, false><<<pgrid, 256, 0, g->stream>>>(pa);
       LUXB_CUDA(cudaGetLastError());
       g->stats.kernel_launches++;
     }
@@ -1798,14 +1855,16 @@ static int pagerank_publish(luxb_graph* g, float* x_new) {
       g->stats.kernel_launches++;
       return 0;
     };
-    if (g->overlap_exchange) {
+    if (g->direct_push) {
+      // everything is already in place: the owners stored into every rank's transfer array
+    } else if (g->overlap_exchange) {
       LUXB_CUDA(cudaEventRecord(g->ev_pack, g->stream));  // = "barrier passed"
+      LUXB_TRY(pull(0, Ch, g->stream, g->num_sms * 2));   // first in line: the next panel kernel waits for it
       LUXB_CUDA(cudaStreamWaitEvent(g->stream2, g->ev_pack, 0));
       // beside the panel kernel: only the SMs that kernel leaves free (launch_seg_shape)
       LUXB_TRY(pull(cold_base, Cc, g->stream2, std::max(2 * g->panel_reserve_sms, 8)));
       LUXB_CUDA(cudaEventRecord(g->ev_cold, g->stream2));
       g->cold_pending = true;
-      LUXB_TRY(pull(0, Ch, g->stream, g->num_sms * 2));
     } else {
       LUXB_TRY(pull(0, Ch, g->stream, g->num_sms * 2));
       LUXB_TRY(pull(cold_base, Cc, g->stream, g->num_sms * 2));
@@ -2142,11 +2201,20 @@ static int one_iteration(luxb_graph* g) {
 static int finish_timed(luxb_graph* g) {
   LUXB_TRY(wait_cold_exchange(g));  // the loop time includes the overlapped part of the last exchange
   pt_flush(g);
+  if (g->pt.per_call) {  // LUXB_PHASE_TIMING=2: one line per luxb_iterate call instead of one per handle
+    pt_print(g);
+    for (double& v : g->pt.sum) v = 0;
+    g->pt.cnt = 0;
+  }
   LUXB_CUDA(cudaEventRecord(g->ev_end, g->stream));
   LUXB_CUDA(cudaStreamSynchronize(g->stream));
   float ms = 0.f;
   LUXB_CUDA(cudaEventElapsedTime(&ms, g->ev_begin, g->ev_end));
   g->stats.loop_seconds += ms * 1e-3;
+  if (g->h_barrier_err && *g->h_barrier_err) {
+    set_error("iteration barrier: rank %u never arrived (10 s)", *g->h_barrier_err - 1u);
+    return LUXB_ERR_STATE;
+  }
   for (size_t k = 0; k + 1 < g->kt_used; k += 2) {
     float kms = 0.f;
     LUXB_CUDA(cudaEventElapsedTime(&kms, g->kt_events[k], g->kt_events[k + 1]));
@@ -2168,6 +2236,7 @@ int luxb_iterate(luxb_graph* g, int iters, uint64_t* active_out) {
   if (!g->inited) { set_error("luxb_iterate before luxb_init"); return LUXB_ERR_STATE; }
   LUXB_ARG(iters >= 0, "negative iteration count");
   LUXB_CUDA(cudaSetDevice(g->cfg.device));
+  if (const char* env = getenv("LUXB_PHASE_TIMING")) { g->pt.on = atoi(env) != 0; g->pt.per_call = atoi(env) == 2; }  // may change between calls
   LUXB_CUDA(cudaEventRecord(g->ev_begin, g->stream));
   for (int i = 0; i < iters; ++i) {
     LUXB_TRY(one_iteration(g));
@@ -2395,17 +2464,7 @@ int luxb_get_local_csc(luxb_graph* g, luxb_eid* row_end_abs, luxb_vid* src, int3
 
 void luxb_close(luxb_graph* g) {
   if (!g) return;
-  if (g->pt.on && g->pt.cnt) {
-    char line[1024];
-    int n = snprintf(line, sizeof(line), "[luxb rank %d] phase means over %ld iterations:", g->cfg.rank, g->pt.cnt);
-    double sum = 0;
-    for (int k = 0; k < 9; ++k) {
-      n += snprintf(line + n, sizeof(line) - n, " %s %.3f ms;", kPhaseName[k], g->pt.sum[k] / g->pt.cnt);
-      sum += g->pt.sum[k] / g->pt.cnt;
-    }
-    snprintf(line + n, sizeof(line) - n, " sum %.3f ms\n", sum);
-    fputs(line, stderr);  // one write per rank: the ranks' lines do not interleave
-  }
+  pt_print(g);
   cudaSetDevice(g->cfg.device);
   if (g->stream) cudaStreamSynchronize(g->stream);
   if (g->d_hot) cudaCtxResetPersistingL2Cache();  // release the lines pinned for the hot copies
@@ -2431,8 +2490,9 @@ void luxb_close(luxb_graph* g) {
   if (g->d_hub_vtx) cudaFree(g->d_hub_vtx);
   if (g->d_hub_bits) cudaFree(g->d_hub_bits);
   if (g->d_sb_partial) cudaFree(g->d_sb_partial);
-  for (void* q : {(void*)g->d_zperm, (void*)g->d_pack_list, (void*)g->d_xt[0], (void*)g->d_xt[1], (void*)g->d_fctl, (void*)g->d_slot_off})
+  for (void* q : {(void*)g->d_zperm, (void*)g->d_pack_list, (void*)g->d_xt[0], (void*)g->d_xt[1], (void*)g->d_fctl, (void*)g->d_slot_off, (void*)g->d_flags})
     if (q) cudaFree(q);
+  if (g->h_barrier_err) cudaFreeHost(g->h_barrier_err);
   if (g->h_hdr) cudaFreeHost(g->h_hdr);
   if (g->h_scratch) cudaFreeHost(g->h_scratch);
   for (cudaEvent_t e : g->kt_events) cudaEventDestroy(e);

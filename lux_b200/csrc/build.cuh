@@ -359,19 +359,50 @@ struct PackPushArgs {
   uint64_t hot_chunk, cold_chunk; // equal chunk sizes (elements) of the two regions
   uint64_t cold_base;             // offset of the cold region inside XT
   T* xt[LUXB_MAX_PARTS];          // every rank's transfer array (own rank included)
+  int P;
 };
-template <class T>
+// kDirect: every owned entry goes to EVERY rank's transfer array (P coalesced store streams; no pull step afterwards)
+template <class T, bool kDirect>
 __global__ void pack_push_kernel(const __grid_constant__ PackPushArgs<T> a) {
   const uint64_t n = (uint64_t)a.n_hot + a.n_cold;
   for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
     const T v = a.x_local[a.list[k]];
-    if (k < a.n_hot) {
-      const uint64_t pos = a.hot_pos0 + k;
-      a.xt[pos / a.hot_chunk][pos] = v;
+    const bool hot = k < a.n_hot;
+    const uint64_t pos = hot ? a.hot_pos0 + k : a.cold_pos0 + (k - a.n_hot);
+    const uint64_t at = hot ? pos : a.cold_base + pos;
+    if constexpr (kDirect) {
+      for (int q = 0; q < a.P; ++q) a.xt[q][at] = v;
     } else {
-      const uint64_t pos = a.cold_pos0 + (k - a.n_hot);
-      a.xt[pos / a.cold_chunk][a.cold_base + pos] = v;
+      a.xt[pos / (hot ? a.hot_chunk : a.cold_chunk)][at] = v;
     }
+  }
+}
+
+// Barrier between the ranks of one box without a library call or a host round trip: lane k stores this barrier's epoch
+// into word `me` of rank k's flag array (system-scope release, over NVLink) and spins on word k of its own array.  The
+// kernels before it in the stream have completed, so their remote stores are ordered before the flag (release is
+// cumulative); kernels after it see what the peers wrote before THEIR flag stores.  A peer that never arrives (its
+// process died) releases the spin after 10 s with *err set — the GPU is never left hanging.
+struct FlagBarrierArgs {
+  uint32_t* peer[LUXB_MAX_PARTS];  // every rank's flag array
+  uint32_t* mine;
+  uint32_t* err;
+  int P, me;
+  uint32_t epoch;
+};
+__global__ void flag_barrier_kernel(const __grid_constant__ FlagBarrierArgs a) {
+  const int k = threadIdx.x;
+  if (k >= a.P || k == a.me) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.peer[k] + a.me), "r"(a.epoch) : "memory");
+  uint64_t t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    uint32_t f;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(a.mine + k) : "memory");
+    if ((int32_t)(f - a.epoch) >= 0) break;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > 10000000000ull) { *a.err = 1u + (uint32_t)k; break; }
   }
 }
 
@@ -391,18 +422,24 @@ struct ChunkPullArgs {
   int P, me;
 };
 __global__ void __launch_bounds__(512) chunk_pull_kernel(const __grid_constant__ ChunkPullArgs a) {
-  constexpr uint64_t kSlab = 4096;  // float4 per slab
+  constexpr int kDepth = 8;                  // 128-bit peer loads in flight per thread: NVLink latency, not issue, is the bound
+  constexpr uint64_t kSlab = 512 * kDepth;   // float4 per slab
   const uint64_t v4 = a.chunk / 4;
   const uint64_t slabs_per_chunk = (v4 + kSlab - 1) / kSlab;
   const uint64_t units = slabs_per_chunk * (uint64_t)(a.P - 1);
   for (uint64_t u = blockIdx.x; u < units; u += gridDim.x) {
     const int q = (int)(u % (uint64_t)(a.P - 1));
     const int k = q < a.me ? q : q + 1;
-    const uint64_t j0 = (u / (uint64_t)(a.P - 1)) * kSlab;
-    const uint64_t j1 = j0 + kSlab < v4 ? j0 + kSlab : v4;
+    const uint64_t j0 = (u / (uint64_t)(a.P - 1)) * kSlab + threadIdx.x;
     const float4* s = reinterpret_cast<const float4*>(a.src[k] + (uint64_t)k * a.chunk);
     float4* d = reinterpret_cast<float4*>(a.dst + (uint64_t)k * a.chunk);
-    for (uint64_t j = j0 + threadIdx.x; j < j1; j += blockDim.x) d[j] = s[j];
+    float4 r[kDepth];
+#pragma unroll
+    for (int i = 0; i < kDepth; ++i)
+      if (j0 + (uint64_t)i * 512 < v4) r[i] = s[j0 + (uint64_t)i * 512];
+#pragma unroll
+    for (int i = 0; i < kDepth; ++i)
+      if (j0 + (uint64_t)i * 512 < v4) d[j0 + (uint64_t)i * 512] = r[i];
   }
 }
 

@@ -38,7 +38,7 @@ struct PullLayout {
 
 // dev aid: LUXB_PHASE_TIMING=1 prints the mean device time of each phase of a PageRank iteration at luxb_close
 struct PhaseTimer {
-  bool on = false;
+  bool on = false, per_call = false;
   std::vector<cudaEvent_t> ev;
   std::vector<int> tag;
   double sum[12] = {0};
@@ -144,6 +144,14 @@ struct luxb_graph {
   void* peer_val[2][LUXB_MAX_PARTS]{};  // imported replicas of the peers (P2P exchange)
   void* peer_fq[LUXB_MAX_PARTS]{};      // imported frontier slot tables of the peers (CC / SSSP P2P push)
   uint32_t* d_sync = nullptr;
+  // iteration barrier of the P2P paths without a library call: every rank owns P flag words, peers store their barrier
+  // epoch into "their" word over NVLink and spin on their own (flag_barrier_kernel, build.cuh)
+  uint32_t* d_flags = nullptr;
+  void* peer_flags[LUXB_MAX_PARTS]{};
+  uint32_t barrier_epoch = 0;
+  uint32_t* h_barrier_err = nullptr;  // mapped pinned word: set when a peer never arrived (10 s)
+  bool flag_barrier = true;           // LUXB_BARRIER=nccl: the 4-byte all-reduce of the communicator instead
+  bool direct_push = false;           // LUXB_PUSH=direct: owners store into EVERY rank's transfer array, no chunk pulls
   uint64_t ag_chunk = 0, hot_chunk = 0;  // equal chunk sizes (elements) of the balanced all-gather
 
   // source-blocked PageRank sweep (panel.cuh): hub destinations x hot source blocks in shared memory
