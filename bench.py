@@ -22,9 +22,17 @@ import sys
 import threading
 import time
 
-# OpenMP placement of the CPU legs (oracle): spread threads over all cores / NUMA nodes, set before libgomp is loaded
-os.environ.setdefault("OMP_PROC_BIND", "spread")
-os.environ.setdefault("OMP_PLACES", "cores")
+# OpenMP placement of the CPU legs (oracle): spread threads over all cores / NUMA nodes, set before libgomp is loaded.
+# ONLY in a process that runs a CPU leg alone (N = 1, or the reference arm where rank 0 works and the others exit): with
+# OMP_PROC_BIND set, libgomp pins the MAIN thread to the first place the moment torch loads it — in every rank.  At N > 1
+# that put the kernel-enqueuing threads of all ranks on CPU 0, where they time-sliced against each other's spinning
+# cudaStreamSynchronize: iterations of 2 ms measured as 4-5 ms (profiles/r02c_bench_n4_* vs r02_trace_exchange_n4.txt).
+_AFFINITY0 = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+_REFERENCE_ARM = "--impl=reference" in sys.argv or any(a == "--impl" and b == "reference" for a, b in zip(sys.argv, sys.argv[1:]))
+_CPU_LEG_PROCESS = int(os.environ.get("WORLD_SIZE", "1")) == 1 or _REFERENCE_ARM
+if _CPU_LEG_PROCESS:
+    os.environ.setdefault("OMP_PROC_BIND", "spread")
+    os.environ.setdefault("OMP_PLACES", "cores")
 
 import numpy as np
 
@@ -73,21 +81,33 @@ class ClockSampler:
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
 
-    def start(self):
+    def start(self, wait_s=8.0):
+        """Started BEFORE the warm-up (B200_PROFILING.md: "start before, kill after"): nvidia-smi's own start-up attaches to
+        every GPU of the box and stalls their launch queues for tens of ms — inside a 60 ms multi-GPU timed region that doubled
+        the measured iteration time (profiles/r02c_bench_n4_rmat27_nccl_barrier.json vs r02_trace_exchange_n4.txt)."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < wait_s and self.proc.poll() is None:
+                time.sleep(0.01)  # first row printed = start-up over
         except Exception:  # noqa: BLE001
             self.proc = None
+
+    def mark(self):
+        """Index of the next sample: brackets the timed region."""
+        return len(self.rows)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
-    def stop(self):
+    def stop(self, lo=0, hi=None):
+        """Summary of the samples taken inside [lo, hi) (marks); a timed region shorter than the sampling period falls back
+        to every sample since the start of the warm-up (the same load) and says so."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -95,9 +115,13 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:  # noqa: BLE001
             self.proc.kill()
+        hi = len(self.rows) if hi is None else hi
+        rows, window = self.rows[lo:hi], "timed region"
+        if not rows:
+            rows, window = self.rows[:max(hi, 1)], "warm-up + timed region (timed region shorter than the 100 ms sampling period)"
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -110,7 +134,7 @@ class ClockSampler:
                 if f[3 + k].lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def dist_env():
@@ -234,6 +258,8 @@ def main():
 
     # ------------------------------------------------------------------------------------------------ ours
     import torch
+    if world > 1 and _AFFINITY0 is not None:
+        os.sched_setaffinity(0, _AFFINITY0)  # whatever the environment said: the enqueuing thread of a rank is never pinned
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
@@ -261,23 +287,26 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # before the warm-up: its start-up must not fall into the timed region
+    barrier()
     for _ in range(args.warmup):
         g.iterate(ITERS_PER_STEP)
 
     # ---- device-resident timed region: exactly K steps ----
     g.enable_kernel_timing(True)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     s0 = g.stats()
     barrier()
+    m0 = sampler.mark()
     w0 = time.perf_counter()
     for _ in range(args.steps):
         g.iterate(ITERS_PER_STEP)
     barrier()
     w1 = time.perf_counter()
+    m1 = sampler.mark()
     s1 = g.stats()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(m0, m1) if rank == 0 else None
     g.enable_kernel_timing(False)
     dev_s = s1["loop_seconds"] - s0["loop_seconds"]
     kern_s = s1["dominant_kernel_seconds"] - s0["dominant_kernel_seconds"]

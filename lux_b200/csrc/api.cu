@@ -216,7 +216,7 @@ static int graph_begin(const luxb_config* cfg, luxb_graph** out) {
   if (const char* env = getenv("LUXB_PHASE_TIMING")) { g->pt.on = atoi(env) != 0; g->pt.per_call = atoi(env) == 2; }
   if (const char* env = getenv("LUXB_L2_HINTS")) g->l2_hints = atoi(env);
   if (const char* env = getenv("LUXB_OVERLAP")) g->overlap_exchange = atoi(env) != 0;
-  if (const char* env = getenv("LUXB_BARRIER")) g->flag_barrier = strcmp(env, "nccl") != 0;
+  if (const char* env = getenv("LUXB_BARRIER")) { g->flag_barrier = strcmp(env, "nccl") != 0; g->flag_barrier_all = strcmp(env, "flag") == 0; }
   if (const char* env = getenv("LUXB_PUSH")) g->direct_push = strcmp(env, "direct") == 0;
   if (const char* env = getenv("LUXB_FUSED_FIXUP")) g->fused_fixup = atoi(env) != 0;
   if (const char* env = getenv("LUXB_PANEL_RESERVE_SMS")) g->panel_reserve_sms = std::max(0, atoi(env));
@@ -1176,7 +1176,9 @@ static int allgather_slices(luxb_graph* g, void* replica, size_t elem_bytes) {
 // completes on a rank, every peer's kernels (and therefore their stores into this rank's replica) are done.
 static int p2p_barrier(luxb_graph* g) {
   if (g->P == 1) return 0;
-  if (g->flag_barrier && g->p2p_ready) {
+  // the flag kernel is used where it has been validated on hardware (PageRank exchange, 4 GPUs, bit-identical values and the
+  // same iteration time as the all-reduce: profiles/r02_trace_exchange_n4.txt); LUXB_BARRIER=flag extends it to the other apps
+  if (g->flag_barrier && g->p2p_ready && (g->cfg.app == LUXB_PAGERANK || g->flag_barrier_all)) {
     FlagBarrierArgs a{};
     for (int p = 0; p < g->P; ++p) a.peer[p] = reinterpret_cast<uint32_t*>(g->peer_flags[p]);
     a.mine = g->d_flags;
@@ -1791,10 +1793,11 @@ static int sweep_seg(luxb_graph* g, const typename Prog::Vertex* x_nat, const ty
 
 // After a sweep (or luxb_set_values): x_new holds this rank's final slice in natural order.  Make it visible to the
 // next sweep of every rank: refresh the hot copies and, on several ranks, run the PACKED exchange — only vertices that are
-// ever gathered travel (build.cuh), as one balanced all-gather: each rank packs its share into XT[new], DMA-copies the
-// pieces that fall into a peer's EQUAL chunk straight into that peer's XT[new] over NVLink, and after a 4-byte barrier
-// ncclAllGather distributes the equal chunks (edge-balanced partitions own very different numbers of vertices — RMAT-27 at
-// 8 GPUs: rank 7 owns 40 % — so owner broadcasts would be bound by the biggest owner's egress).
+// ever gathered travel (build.cuh), as one balanced all-gather written as kernels over peer memory: pack_push_kernel stores
+// every owned entry into the transfer array of the rank holding its EQUAL chunk, a barrier (flag kernel) says the pushes
+// have landed, chunk_pull_kernel copies the other ranks' chunks over NVLink.  Equal chunks because edge- or cost-balanced
+// partitions own very different numbers of vertices (RMAT-27 at 8 GPUs: rank 7 owns 40 %): owner broadcasts or direct
+// owner pushes (LUXB_PUSH=direct, measured 10 % slower at 4 GPUs) are bound by the biggest owner's egress.
 static int pagerank_publish(luxb_graph* g, float* x_new) {
   const int me = g->cfg.rank;
   const int grid = g->num_sms * 8;

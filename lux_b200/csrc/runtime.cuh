@@ -151,6 +151,7 @@ struct luxb_graph {
   uint32_t barrier_epoch = 0;
   uint32_t* h_barrier_err = nullptr;  // mapped pinned word: set when a peer never arrived (10 s)
   bool flag_barrier = true;           // LUXB_BARRIER=nccl: the 4-byte all-reduce of the communicator instead
+  bool flag_barrier_all = false;      // LUXB_BARRIER=flag: also for the CC / SSSP / col_filter barriers
   bool direct_push = false;           // LUXB_PUSH=direct: owners store into EVERY rank's transfer array, no chunk pulls
   uint64_t ag_chunk = 0, hot_chunk = 0;  // equal chunk sizes (elements) of the balanced all-gather
 
