@@ -218,6 +218,7 @@ static int graph_begin(const luxb_config* cfg, luxb_graph** out) {
   if (const char* env = getenv("LUXB_OVERLAP")) g->overlap_exchange = atoi(env) != 0;
   if (const char* env = getenv("LUXB_BARRIER")) { g->flag_barrier = strcmp(env, "nccl") != 0; g->flag_barrier_all = strcmp(env, "flag") == 0; }
   if (const char* env = getenv("LUXB_PUSH")) g->direct_push = strcmp(env, "direct") == 0;
+  if (const char* env = getenv("LUXB_BARRIER_TIMEOUT_S")) g->barrier_timeout_ns = (uint64_t)std::max(1, atoi(env)) * 1000000000ull;
   if (const char* env = getenv("LUXB_FUSED_FIXUP")) g->fused_fixup = atoi(env) != 0;
   if (const char* env = getenv("LUXB_PANEL_RESERVE_SMS")) g->panel_reserve_sms = std::max(0, atoi(env));
   return 0;
@@ -1186,6 +1187,7 @@ static int p2p_barrier(luxb_graph* g) {
     a.P = g->P;
     a.me = g->cfg.rank;
     a.epoch = ++g->barrier_epoch;
+    a.timeout_ns = g->barrier_timeout_ns;
     flag_barrier_kernel<<<1, LUXB_MAX_PARTS, 0, g->stream>>>(a);
     LUXB_CUDA(cudaGetLastError());
     g->stats.kernel_launches++;
@@ -2215,7 +2217,8 @@ static int finish_timed(luxb_graph* g) {
   LUXB_CUDA(cudaEventElapsedTime(&ms, g->ev_begin, g->ev_end));
   g->stats.loop_seconds += ms * 1e-3;
   if (g->h_barrier_err && *g->h_barrier_err) {
-    set_error("iteration barrier: rank %u never arrived (10 s)", *g->h_barrier_err - 1u);
+    set_error("iteration barrier: rank %u did not arrive within %llu s (LUXB_BARRIER_TIMEOUT_S)", *g->h_barrier_err - 1u,
+              (unsigned long long)(g->barrier_timeout_ns / 1000000000ull));
     return LUXB_ERR_STATE;
   }
   for (size_t k = 0; k + 1 < g->kt_used; k += 2) {

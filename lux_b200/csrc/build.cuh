@@ -382,13 +382,15 @@ __global__ void pack_push_kernel(const __grid_constant__ PackPushArgs<T> a) {
 // into word `me` of rank k's flag array (system-scope release, over NVLink) and spins on word k of its own array.  The
 // kernels before it in the stream have completed, so their remote stores are ordered before the flag (release is
 // cumulative); kernels after it see what the peers wrote before THEIR flag stores.  A peer that never arrives (its
-// process died) releases the spin after 10 s with *err set — the GPU is never left hanging.
+// process died) releases the spin after timeout_ns (30 s, LUXB_BARRIER_TIMEOUT_S) with *err set — the GPU is never left
+// hanging.
 struct FlagBarrierArgs {
   uint32_t* peer[LUXB_MAX_PARTS];  // every rank's flag array
   uint32_t* mine;
   uint32_t* err;
   int P, me;
   uint32_t epoch;
+  uint64_t timeout_ns;
 };
 __global__ void flag_barrier_kernel(const __grid_constant__ FlagBarrierArgs a) {
   const int k = threadIdx.x;
@@ -402,7 +404,7 @@ __global__ void flag_barrier_kernel(const __grid_constant__ FlagBarrierArgs a) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(a.mine + k) : "memory");
     if ((int32_t)(f - a.epoch) >= 0) break;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    if (t - t0 > 10000000000ull) { *a.err = 1u + (uint32_t)k; break; }
+    if (t - t0 > a.timeout_ns) { *a.err = 1u + (uint32_t)k; break; }
   }
 }
 

@@ -149,7 +149,8 @@ struct luxb_graph {
   uint32_t* d_flags = nullptr;
   void* peer_flags[LUXB_MAX_PARTS]{};
   uint32_t barrier_epoch = 0;
-  uint32_t* h_barrier_err = nullptr;  // mapped pinned word: set when a peer never arrived (10 s)
+  uint32_t* h_barrier_err = nullptr;  // mapped pinned word: set when a peer did not arrive in time
+  uint64_t barrier_timeout_ns = 30000000000ull;
   bool flag_barrier = true;           // LUXB_BARRIER=nccl: the 4-byte all-reduce of the communicator instead
   bool flag_barrier_all = false;      // LUXB_BARRIER=flag: also for the CC / SSSP / col_filter barriers
   bool direct_push = false;           // LUXB_PUSH=direct: owners store into EVERY rank's transfer array, no chunk pulls
