@@ -110,13 +110,16 @@ def test_one_barrier_per_iteration_with_double_buffering_is_race_free(P, hot_cou
     xt = [[torch.full((n,), -1, dtype=torch.int64).share_memory_() for _ in range(2)] for _ in range(P)]
     flags = [torch.zeros(P, dtype=torch.int64).share_memory_() for _ in range(P)]
     errors = torch.full((P,), -3, dtype=torch.int64).share_memory_()
-    ctx = mp.get_context("fork")
+    ctx = mp.get_context("spawn")
     procs = [ctx.Process(target=_rank, args=(r, P, hot_off, cold_off, Ch, Cc, xt, flags, 40, 5, errors)) for r in range(P)]
     for p in procs:
         p.start()
     for p in procs:
-        p.join(120)
-        assert not p.is_alive()
+        p.join(180)
+    alive = [p for p in procs if p.is_alive()]
+    for p in alive:
+        p.terminate()
+    assert not alive
     assert errors.tolist() == [0] * P, errors.tolist()
 
 
