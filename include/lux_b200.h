@@ -56,8 +56,9 @@ typedef enum {
                              owner (grouped ncclBroadcast); CC / SSSP broadcast frontier slots and label slices;
                              col_filter all-gathers the vector slices.  Needs no peer mappings */
   LUXB_EXCHANGE_P2P = 1,  /* peer memory over NVLink (luxb_p2p_export / import): PageRank = pack+push to the equal-chunk
-                             holders, 4-byte barrier, chunk pull (balanced all-gather in three kernels, cold half
-                             overlapped on a second stream); CC / SSSP = frontier P2P push into the peers' slot tables
+                             holders, flag barrier kernel (system-scope release / acquire on peer flag words),
+                             chunk pull — a balanced all-gather without a library call, cold half overlapped on a
+                             second stream; CC / SSSP = frontier P2P push into the peers' slot tables
                              and label replicas; col_filter = peer stores of the new vectors */
   LUXB_EXCHANGE_P2P_FUSED = 2 /* kept for source compatibility: same as LUXB_EXCHANGE_P2P (round 1's fused stores from the
                              gather kernel lost at 8 GPUs and are gone) */
