@@ -32,7 +32,6 @@ struct CudaFail { int code; };
     if (_rc != 0) return _rc;     \
   } while (0)
 
-static inline uint64_t ceil_div_u64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
 
 // ---- device helpers -----------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
