@@ -783,6 +783,7 @@ int luxb_p2p_disconnect(luxb_graph* g) {
   LUXB_ARG(g != nullptr, "graph is NULL");
   LUXB_CUDA(cudaSetDevice(g->cfg.device));
   if (g->stream) LUXB_CUDA(cudaStreamSynchronize(g->stream));
+  if (g->stream2) LUXB_CUDA(cudaStreamSynchronize(g->stream2));  // a cold pull may still be reading the peers' transfer arrays
   p2p_unmap(g);
   return 0;
 }
@@ -2473,6 +2474,7 @@ void luxb_close(luxb_graph* g) {
   pt_print(g);
   cudaSetDevice(g->cfg.device);
   if (g->stream) cudaStreamSynchronize(g->stream);
+  if (g->stream2) cudaStreamSynchronize(g->stream2);
   if (g->d_hot) cudaCtxResetPersistingL2Cache();  // release the lines pinned for the hot copies
   p2p_unmap(g);
   if (g->stream2) cudaStreamSynchronize(g->stream2);
