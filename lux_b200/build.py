@@ -1,5 +1,6 @@
 """In-tree build of libluxb.so (hand-written sm_100a CUDA + the C ABI).  nvcc cross-compiles without a GPU."""
 import fcntl
+import hashlib
 import os
 import subprocess
 
@@ -16,9 +17,28 @@ def _sources():
         os.path.join(_HERE, "..", "include", "lux_b200.h")]
 
 
+HASH = LIB + ".srchash"
+
+
+def source_hash():
+    """Digest of everything the library is built from (source names + contents + compiler flags)."""
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for s in _sources():
+        h.update(os.path.basename(s).encode() + b"\0")
+        with open(s, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def is_stale():
+    """The library is current when the digest written next to it at build time equals the digest of the sources — file
+    times do not survive every copy of the tree (a snapshot sent to a GPU box), contents do.  A library without a digest
+    file (built by hand) falls back to the file-time rule."""
     if not os.path.exists(LIB):
         return True
+    if os.path.exists(HASH):
+        with open(HASH) as f:
+            return f.read().strip() != source_hash()
     t = os.path.getmtime(LIB)
     return any(os.path.getmtime(s) > t for s in _sources())
 
@@ -39,8 +59,12 @@ def build(force=False, verbose=False):
             tmp = LIB + ".tmp.%d" % os.getpid()
             cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp, os.path.join(CSRC, "api.cu"), "-ldl"]
             try:
+                digest = source_hash()  # of what the compiler is about to read
                 subprocess.check_call(cmd, cwd=CSRC)
                 os.replace(tmp, LIB)
+                with open(HASH + ".tmp.%d" % os.getpid(), "w") as f:
+                    f.write(digest + "\n")
+                os.replace(HASH + ".tmp.%d" % os.getpid(), HASH)
             finally:
                 if os.path.exists(tmp):
                     os.remove(tmp)
